@@ -1,0 +1,171 @@
+/*
+ * b200jk.h -- C ABI of the B200-native density-fitted J/K engine (libb200jk.so).
+ *
+ * This is the drop-in boundary behind psi4's MEM_DF JK object.  Every entry point names the
+ * reference interface it replaces (paths relative to psi4/src/psi4/ in the psi4 tree).
+ * Plain C types only: no C++ classes, no exceptions, no torch types.  All matrices are
+ * row-major contiguous doubles, exactly what psi4's Matrix::get_pointer() / pointer()[0]
+ * hands out for a C1 matrix (libmints/matrix.h:553).
+ *
+ * Call order for one SCF:
+ *     b200jk_create[_rank]            <- MemDFJK ctor / DFHelper ctor      (libfock/MemDFJK.cc:56-64)
+ *     b200jk_set_layout               <- DFHelper::prepare_sparsity tables (lib3index/dfhelper.cc:299-420)
+ *     b200jk_upload | _upload_rows    <- Ppq_/m1Ppq_/wPpq_ after prepare_AO_core (:514-588, :589-699)
+ *     b200jk_compute  (every iteration) <- DFHelper::build_JK              (:3015-3043)
+ *     b200jk_destroy
+ *
+ * Threading: calls on one handle must be serialised by the caller (as JK::compute is, from the
+ * Python main thread).  Several handles may coexist (the SAD guess builds its own JK, sad.cc:706).
+ *
+ * There is no CPU fallback: if no CUDA device / insufficient HBM, calls fail with an error code
+ * (mirrors SCF_SUBTYPE=INCORE throwing at dfhelper.cc:259-262 rather than degrading).
+ */
+#ifndef B200JK_H
+#define B200JK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200jk b200jk_t;
+
+/* Status codes (psi4 glue turns non-zero into PSIEXCEPTION, libpsi4util/exception.h:48). */
+enum {
+    B200JK_OK = 0,
+    B200JK_ERR_INVALID = 1,  /* bad argument / call order                      */
+    B200JK_ERR_CUDA = 2,     /* CUDA runtime error (message in last_error)     */
+    B200JK_ERR_OOM = 3,      /* tensor + work buffers do not fit in HBM        */
+    B200JK_ERR_NCCL = 4,     /* NCCL error                                     */
+    B200JK_ERR_NODEVICE = 5  /* no CUDA device: engine refuses to run          */
+};
+
+/* Which three-index tensor (lib3index/dfhelper.h:380,385-386). */
+enum {
+    B200JK_TENSOR_PPQ = 0,   /* Ppq_   = J^-1/2 (A|mn)            J and K      */
+    B200JK_TENSOR_M1PPQ = 1, /* m1Ppq_ = J^-1   (A|mn)            wK left      */
+    B200JK_TENSOR_WPPQ = 2   /* wPpq_  = (A|erf(w r)/r|mn)        wK right     */
+};
+
+#define B200JK_NCCL_ID_BYTES 128
+
+/* ---- construction --------------------------------------------------------------------------- */
+
+/* One process driving `ngpu` devices (psi4 is single-process: libfock/jk.cc:143-150 constructs
+ * exactly one MemDFJK).  The auxiliary index Q is split into ngpu contiguous shards; partial
+ * J/K/wK are summed with one NCCL all-reduce per build.  dev_ids may be NULL (0..ngpu-1). */
+int b200jk_create(b200jk_t** out, int ngpu, const int* dev_ids);
+
+/* One process per GPU (torchrun-style launch): this rank owns Q shard `rank` of `world`.
+ * nccl_id: B200JK_NCCL_ID_BYTES bytes from b200jk_nccl_unique_id() on rank 0, broadcast by the
+ * caller (ignored when world == 1). */
+int b200jk_create_rank(b200jk_t** out, int device, int rank, int world, const void* nccl_id);
+int b200jk_nccl_unique_id(void* out_bytes /* B200JK_NCCL_ID_BYTES */);
+
+void b200jk_destroy(b200jk_t* h);
+
+/* ---- layout + tensor upload ------------------------------------------------------------------ */
+
+/* Tables of DFHelper::prepare_sparsity (dfhelper.cc:377-398), passed verbatim:
+ *   small_skips[nbf+1]  small_skips_    sp(m), last entry = total kept pairs
+ *   big_skips[nbf+1]    big_skips_      offset of row-block m in the packed tensor (naux*sp(m) each)
+ *   fun_index[nbf*nbf]  schwarz_fun_index_  1-based rank of n among kept partners of m, 0 = dropped
+ * Element B(Q,m,n) lives at host_pQq[big_skips[m] + Q*sp(m) + fun_index[m*nbf+n] - 1]
+ * (dfhelper.cc:1274-1276, :1671-1672).  The diagonal must be kept (assumed at :3213). */
+int b200jk_set_layout(b200jk_t* h, size_t nbf, size_t naux, const size_t* small_skips, const size_t* big_skips,
+                      const size_t* fun_index);
+
+/* Copy a whole host tensor (big_skips[nbf] doubles) into HBM, Q-sharded.  The host buffer is not
+ * retained; psi4 may release Ppq_ afterwards. */
+int b200jk_upload(b200jk_t* h, int which, const double* host_pQq);
+
+/* Streaming variant for the p-blocked construction loop of prepare_AO_core (:540-587): rows
+ * m in [m0, m1) only; host_rows points at the first double of row-block m0, i.e. what psi4 holds
+ * at Ppq_ + big_skips[m0]. */
+int b200jk_upload_rows(b200jk_t* h, int which, size_t m0, size_t m1, const double* host_rows);
+
+/* ---- the hot path ----------------------------------------------------------------------------- */
+
+/* DFHelper::build_JK (dfhelper.cc:3015-3043) + the zero()/hermitivitize() wrapper of
+ * MemDFJK::compute_JK (libfock/MemDFJK.cc:97-111).
+ *   nmat            number of (C_left, C_right, D) triples (C_left_ao_.size())
+ *   Cl[i], Cr[i]    nbf x nocc[i], row-major, ld = nocc[i].  Cr == NULL  <=> lr_symmetric_
+ *                   (jk.cc:597-602): K uses T2=T1 (:3367-3368), J uses the upper triangle of D (:3188).
+ *   nocc[i]         Cleft[i]->colspi()[0]; 0 => K[i]/wK[i] left zero (:3354-3357)
+ *   D[i]            nbf x nbf density built by the caller (jk.cc:314-354); only read if do_J
+ *   J[i],K[i],wK[i] nbf x nbf outputs, OVERWRITTEN with the result (the reference zeroes them in
+ *                   MemDFJK.cc:100 and accumulates with beta=1; the sum is identical).  Arrays for
+ *                   untasked products may be NULL.
+ *   wK              requires tensors M1PPQ and WPPQ; symmetrised (A+A^T)/2 when lr_symmetric
+ *                   (MemDFJK.cc:104-110).
+ * Host pointers are not retained past the call. */
+int b200jk_compute(b200jk_t* h, int nmat, const double* const* Cl, const double* const* Cr, const int* nocc,
+                   const double* const* D, double* const* J, double* const* K, double* const* wK, int do_J,
+                   int do_K, int do_wK);
+
+/* Same build with every operand already resident in this rank's HBM (device pointers); used by
+ * the kernel-only timing of bench.py and by callers that keep C/D on the GPU.  Rank mode only
+ * (one shard per handle).  Outputs hold the all-reduced result on every rank. */
+int b200jk_compute_device(b200jk_t* h, int nmat, const double* const* dCl, const double* const* dCr,
+                          const int* nocc, const double* const* dD, double* const* dJ, double* const* dK,
+                          double* const* dwK, int do_J, int do_K, int do_wK);
+
+/* ---- introspection ---------------------------------------------------------------------------- */
+
+typedef struct {
+    /* device time (CUDA events on the engine's stream, max over local shards) of the last compute */
+    double ms_total;      /* first kernel to last kernel incl. all-reduce          */
+    double ms_j;          /* J sweeps (K1+K2)                                      */
+    double ms_half;       /* half-transforms (K3)                                  */
+    double ms_kgemm;      /* K GEMM (K4) incl. split-K reduction                   */
+    double ms_allreduce;  /* NCCL all-reduce                                       */
+    double ms_h2d, ms_d2h; /* host<->device copies of C/D and J/K/wK                */
+    /* algorithmic work of the last compute on THIS handle's shards  */
+    double j_bytes;       /* bytes of B the J sweeps must read                     */
+    double half_flops;    /* 2*A*P*o per transform                                 */
+    double half_bytes;    /* 8*A*P read + 8*N*A*o written per transform            */
+    double kgemm_flops;   /* flops executed by the K GEMM (N(N+1)*A*o if symmetric)*/
+    uint64_t launches;    /* kernels launched by the last compute                  */
+    uint64_t hbm_tensor_bytes; /* bytes of HBM holding the packed tensors          */
+    uint64_t hbm_work_bytes;   /* bytes of HBM in work buffers                     */
+    int n_shards;         /* local shards (GPUs driven by this handle)             */
+    int q_begin, q_end;   /* Q range of local shard 0                              */
+} b200jk_stats;
+
+int b200jk_get_stats(const b200jk_t* h, b200jk_stats* out);
+const char* b200jk_last_error(const b200jk_t* h);
+
+/* DFHelper::get_core_size analogue (dfhelper.cc:216-236) for HBM: bytes needed per GPU for the
+ * tensors (+2 more with wK) and work buffers at the given max_nocc; usable before upload. */
+int b200jk_hbm_estimate(const b200jk_t* h, size_t max_nocc, int do_wK, uint64_t* bytes_per_gpu);
+
+/* Limit the HBM the half-transformed intermediate T may take (bytes per GPU; 0 = automatic).
+ * Stands in for DFHelper::set_memory + Qshell_blocks_for_JK_build (:814-869): smaller budgets
+ * make the K build loop over Q chunks. */
+int b200jk_set_work_budget(b200jk_t* h, uint64_t bytes);
+
+/* ---- synthetic workload support (bench.py / large-size tests only; not in the reference) ------ */
+
+/* Fill tensor `which` on the device with value(Q,m,n) = amp[m*nbf+n] * u(seed,Q,min(m,n),max(m,n)),
+ * u in [-1,1) from a counter hash -- bit-identical to oracle_synth_fill() in oracle/dfjk_oracle.c.
+ * Lets C60-size tensors (123 GB) exist without a host copy. */
+int b200jk_fill_synthetic(b200jk_t* h, int which, uint64_t seed, const double* amp /* nbf*nbf host */);
+
+/* Read back rows Q in [q0,q1) of row-block m (packed, sp(m) per row) from local shard holding them. */
+int b200jk_download_rows(b200jk_t* h, int which, size_t m, size_t q0, size_t q1, double* host_out);
+
+/* Device pointer helpers for b200jk_compute_device callers that have no CUDA runtime binding. */
+int b200jk_dev_alloc(b200jk_t* h, size_t bytes, void** dptr);
+int b200jk_dev_free(b200jk_t* h, void* dptr);
+int b200jk_dev_copy(b200jk_t* h, void* dst, const void* src, size_t bytes, int kind /*1=H2D 2=D2H 3=D2D*/);
+
+/* FP64 calibration kernels (register-resident DMMA / DFMA loops) -> TFLOP/s, for the roofline
+ * denominator that MEASURED_PEAKS.json lacks. kind: 0 = DMMA m8n8k4, 1 = DFMA. */
+int b200jk_fp64_peak(b200jk_t* h, int kind, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200JK_H */

@@ -1,0 +1,1087 @@
+// engine.cu -- libb200jk.so: the C ABI of include/b200jk.h over the sm_100a kernels.
+//
+// Host-side orchestration of the in-core DF-JK build (what DFHelper::compute_JK /
+// compute_wK do on the CPU, lib3index/dfhelper.cc:3044-3161, :3378-3438) with the packed
+// (Q|mn) tensor resident in HBM, sharded over the auxiliary index Q.
+//
+// No CPU fallback: every entry point that needs a device fails with an error code if none.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/b200jk.h"
+#include "aux_kernels.cuh"
+#include "dmma_gemm.cuh"
+#include "j_kernels.cuh"
+
+using namespace b2k;
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, resolved lazily (single-GPU handles never touch it).  If the process already has a
+// libnccl.so.2 loaded (e.g. torch's bundled copy) the soname lookup returns that one.
+// ------------------------------------------------------------------------------------------------
+namespace {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+static_assert(sizeof(ncclUniqueId) == B200JK_NCCL_ID_BYTES, "nccl id size");
+struct Nccl {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load(std::string& err) {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+        for (int i = 0; names[i] && !lib; i++) lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) {
+            err = std::string("cannot dlopen libnccl.so.2: ") + dlerror();
+            return false;
+        }
+#define SYM(f)                                                           \
+    *(void**)(&f) = dlsym(lib, "nccl" #f);                               \
+    if (!f) {                                                            \
+        err = "libnccl lacks nccl" #f;                                   \
+        return false;                                                    \
+    }
+        SYM(GetUniqueId) SYM(CommInitRank) SYM(CommInitAll) SYM(CommDestroy) SYM(AllReduce) SYM(GroupStart)
+        SYM(GroupEnd) SYM(GetErrorString)
+#undef SYM
+        return true;
+    }
+};
+Nccl g_nccl;
+constexpr int kNcclDouble = 8;  // ncclFloat64
+constexpr int kNcclSum = 0;
+
+struct Phase {
+    int tag;  // 0 J, 1 half, 2 kgemm, 3 allreduce, 4 h2d, 5 d2h, 6 total
+    cudaEvent_t a, b;
+};
+
+struct Shard {
+    int dev = 0;
+    int q0 = 0, q1 = 0, nq = 0;
+    cudaStream_t stream = nullptr;
+    double* tensor[3] = {nullptr, nullptr, nullptr};
+    size_t tensor_doubles = 0;
+    size_t* d_row_off = nullptr;
+    int *d_ldm = nullptr, *d_sp = nullptr, *d_ign = nullptr, *d_cols = nullptr;
+    size_t* d_cols_off = nullptr;
+    // work buffers (grown on demand, kept across calls: SURVEY.md Appendix B "allocate once per handle")
+    double *in = nullptr, *out = nullptr, *Ctl = nullptr, *Ctr = nullptr, *dpart = nullptr, *dvec = nullptr;
+    double *T1 = nullptr, *T2 = nullptr, *ws = nullptr;
+    size_t in_cap = 0, out_cap = 0, ct_cap = 0, dpart_cap = 0, T_cap = 0, T2_cap = 0, ws_cap = 0;
+    ncclComm_t comm = nullptr;
+    std::vector<Phase> phases;
+    std::vector<cudaEvent_t> evpool;
+    size_t evused = 0;
+    uint64_t launches = 0;
+};
+}  // namespace
+
+struct b200jk {
+    std::vector<Shard> sh;
+    int rank = 0, world = 1;  // rank mode (one shard per process) when world > 1 and sh.size()==1
+    bool rank_mode = false;
+    size_t nbf = 0, naux = 0;
+    bool have_layout = false;
+    bool uploaded[3] = {false, false, false};
+    std::vector<size_t> small_skips, big_skips, row_off_unit;  // row_off_unit: sum of ldm up to m (per q row)
+    std::vector<int> sp, ign, ldm, cols;
+    std::vector<size_t> cols_off;
+    int max_sp = 0;
+    uint64_t work_budget = 0;
+    double* pin_in = nullptr;
+    double* pin_out = nullptr;
+    size_t pin_in_cap = 0, pin_out_cap = 0;
+    std::string err;
+    b200jk_stats stats;
+};
+
+namespace {
+
+int fail(b200jk* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return fail(h, e_ == cudaErrorMemoryAllocation ? B200JK_ERR_OOM : B200JK_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                       \
+    } while (0)
+#define NK(call)                                                                                             \
+    do {                                                                                                     \
+        int r_ = (call);                                                                                     \
+        if (r_ != 0)                                                                                         \
+            return fail(h, B200JK_ERR_NCCL, "%s: %s (%s:%d)", #call, g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T>
+int upload_vec(b200jk* h, T** dptr, const std::vector<T>& v) {
+    if (*dptr) cudaFree(*dptr);
+    *dptr = nullptr;
+    size_t n = std::max<size_t>(v.size(), 1);
+    CK(cudaMalloc((void**)dptr, n * sizeof(T)));
+    if (!v.empty()) CK(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int grow(b200jk* h, double** p, size_t* cap, size_t need) {
+    if (need <= *cap) return 0;
+    if (*p) CK(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    CK(cudaMalloc((void**)p, need * sizeof(double)));
+    *cap = need;
+    return 0;
+}
+
+cudaEvent_t get_event(Shard& s) {
+    if (s.evused == s.evpool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        s.evpool.push_back(e);
+    }
+    return s.evpool[s.evused++];
+}
+struct PhaseScope {
+    Shard& s;
+    Phase ph;
+    PhaseScope(Shard& s_, int tag) : s(s_) {
+        ph.tag = tag;
+        ph.a = get_event(s);
+        ph.b = get_event(s);
+        cudaEventRecord(ph.a, s.stream);
+    }
+    ~PhaseScope() {
+        cudaEventRecord(ph.b, s.stream);
+        s.phases.push_back(ph);
+    }
+};
+
+inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
+
+// Pick the split-K factor of the K GEMM: enough CTAs to fill 148 SMs in nearly whole waves while
+// each split keeps >= 64 k-tiles (prologue/epilogue amortised) and the partial-tile workspace stays bounded.
+void choose_split(int ntiles, int kdim, int nsm, int* nsplit, int* klen) {
+    int nkt = (kdim + BK - 1) / BK;
+    int max_s = std::max(1, nkt / 64);
+    size_t ws_cap = (size_t)1 << 30;  // 1 GiB of partials
+    max_s = (int)std::min<size_t>(max_s, std::max<size_t>(1, ws_cap / ((size_t)ntiles * BM * 128 * 8)));
+    max_s = std::min(max_s, 512);
+    int best = 1;
+    double best_eff = 0;
+    for (int s = 1; s <= max_s; s++) {
+        long ctas = (long)ntiles * s;
+        long waves = (ctas + nsm - 1) / nsm;
+        double eff = (double)ctas / (double)(waves * nsm);
+        if (eff > best_eff + 1e-9) {
+            best_eff = eff;
+            best = s;
+        }
+        if (eff >= 0.97 && waves >= 4) {
+            best = s;
+            break;
+        }
+    }
+    int kl = ((nkt + best - 1) / best) * BK;
+    *klen = kl;
+    *nsplit = (kdim + kl - 1) / kl;
+}
+
+template <int NB>
+int launch_half(b200jk* h, Shard& s, const HalfParams& p, dim3 grid) {
+    static bool attr_set[64] = {false};
+    constexpr size_t smem = gemm_smem_bytes<NB>();
+    if (!attr_set[s.dev]) {
+        CK(cudaFuncSetAttribute(half_transform_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[s.dev] = true;
+    }
+    half_transform_kernel<NB><<<grid, GEMM_THREADS, smem, s.stream>>>(p);
+    s.launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// T[m][q][i] for q in the chunk [qbeg, qbeg+qc): one launch over (i-tiles, q-tiles, m).
+int run_half(b200jk* h, Shard& s, const double* tensor, const double* Ct, int ldc, int o, int op, int qbeg, int qc,
+             double* T) {
+    int nit = (o + 127) / 128;
+    int iw = round_up((op + nit - 1) / nit, 2);
+    int NB = (iw + 15) / 16;
+    HalfParams p;
+    p.tensor = tensor;
+    p.row_off = s.d_row_off;
+    p.ldm = s.d_ldm;
+    p.sp = s.d_sp;
+    p.cols = s.d_cols;
+    p.cols_off = s.d_cols_off;
+    p.Ct = Ct;
+    p.ldc = ldc;
+    p.o = o;
+    p.op = op;
+    p.iw = iw;
+    p.qbeg = qbeg;
+    p.qc = qc;
+    p.nbf = (int)h->nbf;
+    p.T = T;
+    dim3 grid(nit, (qc + BM - 1) / BM, (unsigned)h->nbf);
+    switch (NB) {
+        case 1: return launch_half<1>(h, s, p, grid);
+        case 2: return launch_half<2>(h, s, p, grid);
+        case 3: return launch_half<3>(h, s, p, grid);
+        case 4: return launch_half<4>(h, s, p, grid);
+        case 5: return launch_half<5>(h, s, p, grid);
+        case 6: return launch_half<6>(h, s, p, grid);
+        case 7: return launch_half<7>(h, s, p, grid);
+        default: return launch_half<8>(h, s, p, grid);
+    }
+}
+
+int run_kgemm(b200jk* h, Shard& s, const double* T1, const double* T2, int kdim, bool symmetric, double* Kout) {
+    static bool attr_set[64] = {false};
+    constexpr size_t smem = gemm_smem_bytes<8>();
+    if (!attr_set[s.dev]) {
+        CK(cudaFuncSetAttribute(kgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[s.dev] = true;
+    }
+    int n1d = ((int)h->nbf + BM - 1) / BM;
+    int ntiles = symmetric ? n1d * (n1d + 1) / 2 : n1d * n1d;
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s.dev);
+    int nsplit, klen;
+    choose_split(ntiles, kdim, nsm, &nsplit, &klen);
+    size_t need = (size_t)nsplit * ntiles * BM * 128;
+    int rc = grow(h, &s.ws, &s.ws_cap, need);
+    if (rc) return rc;
+    KgemmParams p;
+    p.T1 = T1;
+    p.T2 = T2;
+    p.nbf = (int)h->nbf;
+    p.kdim = kdim;
+    p.klen = klen;
+    p.ntile1d = n1d;
+    p.symmetric = symmetric ? 1 : 0;
+    p.ws = s.ws;
+    kgemm_kernel<<<dim3(ntiles, nsplit), GEMM_THREADS, smem, s.stream>>>(p);
+    s.launches++;
+    CK(cudaGetLastError());
+    kgemm_reduce_kernel<<<ntiles, 256, 0, s.stream>>>(s.ws, nsplit, ntiles, n1d, p.symmetric, p.nbf, Kout);
+    s.launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int run_j(b200jk* h, Shard& s, const double* D, bool symmetric, double* Jout) {
+    JParams p;
+    p.tensor = s.tensor[B200JK_TENSOR_PPQ];
+    p.row_off = s.d_row_off;
+    p.ldm = s.d_ldm;
+    p.sp = s.d_sp;
+    p.ign = s.d_ign;
+    p.cols = s.d_cols;
+    p.cols_off = s.d_cols_off;
+    p.nbf = (int)h->nbf;
+    p.nq = s.nq;
+    p.symmetric = symmetric ? 1 : 0;
+    p.D = D;
+    p.dpart = s.dpart;
+    p.d = s.dvec;
+    p.J = Jout;
+    static bool attr_set[64] = {false};
+    if (!attr_set[s.dev]) {
+        CK(cudaFuncSetAttribute(j_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(j_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set[s.dev] = true;
+    }
+    size_t sm1 = (size_t)(h->max_sp + 2) * sizeof(double);
+    size_t sm2 = (size_t)s.nq * sizeof(double);
+    if (sm1 > 200 * 1024 || sm2 > 200 * 1024)
+        return fail(h, B200JK_ERR_INVALID, "J kernels: nbf %d / shard naux %d exceed the shared-memory staging limit",
+                    h->max_sp, s.nq);
+    j_dq_kernel<<<dim3((s.nq + J1_ROWS - 1) / J1_ROWS, (unsigned)h->nbf), J_THREADS, sm1, s.stream>>>(p);
+    s.launches++;
+    CK(cudaGetLastError());
+    j_dq_reduce_kernel<<<(s.nq + 127) / 128, 128, 0, s.stream>>>(s.dpart, p.nbf, s.nq, s.dvec);
+    s.launches++;
+    CK(cudaGetLastError());
+    j_mn_kernel<<<dim3((h->max_sp + 127) / 128, (unsigned)h->nbf), J_THREADS, sm2, s.stream>>>(p);
+    s.launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int run_transpose(b200jk* h, Shard& s, const double* C, int o, double* Ct, int ldc, int orows) {
+    dim3 grid((ldc + 31) / 32, (orows + 31) / 32);
+    transpose_c_kernel<<<grid, dim3(32, 8), 0, s.stream>>>(C, (int)h->nbf, o, Ct, ldc, orows);
+    s.launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+struct Task {
+    int nmat;
+    const int* nocc;
+    bool lr, do_J, do_K, do_wK;
+    int max_o;
+    size_t n2;
+    int nprod;  // tasked products
+};
+
+// Grow the per-shard work buffers for this task and pick the Q chunk of the K build.
+int ensure_work(b200jk* h, Shard& s, const Task& t, int* qc_out) {
+    CK(cudaSetDevice(s.dev));
+    int rc;
+    size_t N = h->nbf;
+    if ((rc = grow(h, &s.out, &s.out_cap, (size_t)t.nmat * t.nprod * t.n2))) return rc;
+    if (t.do_J) {
+        if ((rc = grow(h, &s.dpart, &s.dpart_cap, N * (size_t)s.nq + (size_t)s.nq))) return rc;
+        s.dvec = s.dpart + N * (size_t)s.nq;
+    }
+    *qc_out = 0;
+    if ((t.do_K || t.do_wK) && t.max_o > 0) {
+        int op = round_up(t.max_o, 2);
+        int ldc = round_up((int)N, 4);
+        size_t ct = (size_t)round_up(op, 32) * ldc;
+        if (ct > s.ct_cap) {
+            if (s.Ctl) CK(cudaFree(s.Ctl));
+            if (s.Ctr) CK(cudaFree(s.Ctr));
+            s.Ctl = s.Ctr = nullptr;
+            s.ct_cap = 0;
+            CK(cudaMalloc((void**)&s.Ctl, ct * sizeof(double)));
+            CK(cudaMalloc((void**)&s.Ctr, ct * sizeof(double)));
+            s.ct_cap = ct;
+        }
+        bool two = !t.lr || t.do_wK;
+        size_t per_q = N * (size_t)op;  // doubles of T per q row
+        int qc = s.nq;
+        size_t have = std::min(s.T_cap, two ? s.T2_cap : s.T_cap);
+        if (per_q * qc > have) {
+            // need to (re)allocate: budget = user limit or what is free now (+ what we would release)
+            size_t free_b = 0, total_b = 0;
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            size_t reclaim = (s.T_cap + s.T2_cap) * sizeof(double);
+            size_t budget = free_b + reclaim;
+            size_t reserve = ((size_t)1 << 30) + ((size_t)1 << 29);  // split-K partials + slack
+            budget = budget > reserve ? budget - reserve : 0;
+            if (h->work_budget && h->work_budget < budget) budget = h->work_budget;
+            size_t nT = two ? 2 : 1;
+            size_t max_q = budget / (per_q * sizeof(double) * nT);
+            if (max_q < (size_t)qc) {
+                qc = (int)(max_q >= 128 ? (max_q / 128) * 128 : max_q);
+                if (qc < 1)
+                    return fail(h, B200JK_ERR_OOM, "not enough HBM for one Q row of the half-transformed tensor (%zu B)",
+                                per_q * 8 * nT);
+            }
+            if (s.T1) CK(cudaFree(s.T1));
+            if (s.T2) CK(cudaFree(s.T2));
+            s.T1 = s.T2 = nullptr;
+            s.T_cap = s.T2_cap = 0;
+            CK(cudaMalloc((void**)&s.T1, per_q * qc * sizeof(double)));
+            s.T_cap = per_q * qc;
+            if (two) {
+                CK(cudaMalloc((void**)&s.T2, per_q * qc * sizeof(double)));
+                s.T2_cap = per_q * qc;
+            }
+        } else {
+            qc = (int)std::min<size_t>(s.nq, have / per_q);
+        }
+        *qc_out = qc;
+    }
+    return 0;
+}
+
+// All kernels of one build on one shard.  Operands are device pointers on s.dev.
+int run_device(b200jk* h, Shard& s, const Task& t, const double* const* dCl, const double* const* dCr,
+               const double* const* dD, int qc) {
+    CK(cudaSetDevice(s.dev));
+    const size_t N = h->nbf, n2 = t.n2;
+    double* outJ = s.out;
+    double* outK = s.out + (size_t)(t.do_J ? t.nmat : 0) * n2;
+    double* outW = outK + (size_t)(t.do_K ? t.nmat : 0) * n2;
+    CK(cudaMemsetAsync(s.out, 0, (size_t)t.nmat * t.nprod * n2 * sizeof(double), s.stream));
+    int rc;
+    if (t.do_J) {
+        PhaseScope ps(s, 0);
+        for (int i = 0; i < t.nmat; i++)
+            if ((rc = run_j(h, s, dD[i], t.lr, outJ + i * n2))) return rc;
+    }
+    const int ldc = round_up((int)N, 4);
+    for (int pass = 0; pass < 2; pass++) {
+        bool wk = pass == 1;
+        if (wk ? !t.do_wK : !t.do_K) continue;
+        const double* tenL = s.tensor[wk ? B200JK_TENSOR_M1PPQ : B200JK_TENSOR_PPQ];
+        const double* tenR = s.tensor[wk ? B200JK_TENSOR_WPPQ : B200JK_TENSOR_PPQ];
+        for (int i = 0; i < t.nmat; i++) {
+            int o = t.nocc[i];
+            if (!o) continue;  // dfhelper.cc:3354-3357
+            int op = round_up(o, 2);
+            bool one_T = t.lr && !wk;  // T2 = T1 (:3367-3368)
+            {
+                PhaseScope ps(s, 1);
+                if ((rc = run_transpose(h, s, dCl[i], o, s.Ctl, ldc, op))) return rc;
+                if (!one_T && (rc = run_transpose(h, s, t.lr ? dCl[i] : dCr[i], o, s.Ctr, ldc, op))) return rc;
+            }
+            double* Kout = (wk ? outW : outK) + i * n2;
+            for (int qb = 0; qb < s.nq; qb += qc) {
+                int nqc = std::min(qc, s.nq - qb);
+                {
+                    PhaseScope ps(s, 1);
+                    if ((rc = run_half(h, s, tenL, s.Ctl, ldc, o, op, qb, nqc, s.T1))) return rc;
+                    if (!one_T && (rc = run_half(h, s, tenR, s.Ctr, ldc, o, op, qb, nqc, s.T2))) return rc;
+                }
+                {
+                    PhaseScope ps(s, 2);
+                    if ((rc = run_kgemm(h, s, s.T1, one_T ? s.T1 : s.T2, nqc * op, one_T, Kout))) return rc;
+                }
+            }
+            if (wk && t.lr) {
+                hermitivitize_kernel<<<dim3(((unsigned)N + 127) / 128, (unsigned)N), 128, 0, s.stream>>>(Kout, (int)N);
+                s.launches++;
+                CK(cudaGetLastError());
+            }
+        }
+    }
+    return 0;
+}
+
+void account_work(b200jk* h, const Task& t) {
+    // algorithmic work of this handle's shards
+    b200jk_stats& st = h->stats;
+    size_t N = h->nbf;
+    double P = (double)h->small_skips[N];
+    double Ptri = 0;
+    for (size_t m = 0; m < N; m++) Ptri += h->sp[m] - h->ign[m];
+    double Aloc = 0;
+    for (auto& s : h->sh) Aloc += s.nq;
+    st.j_bytes = st.half_flops = st.half_bytes = st.kgemm_flops = 0;
+    for (int i = 0; i < t.nmat; i++) {
+        if (t.do_J) st.j_bytes += 2.0 * 8.0 * Aloc * (t.lr ? Ptri : P);
+        double o = t.nocc[i];
+        if (o == 0) continue;
+        if (t.do_K) {
+            int ntr = t.lr ? 1 : 2;
+            st.half_flops += ntr * 2.0 * Aloc * P * o;
+            st.half_bytes += ntr * (8.0 * Aloc * P + 8.0 * N * Aloc * o);
+            st.kgemm_flops += t.lr ? (double)N * (N + 1) * Aloc * o : 2.0 * N * N * Aloc * o;
+        }
+        if (t.do_wK) {
+            st.half_flops += 2 * 2.0 * Aloc * P * o;
+            st.half_bytes += 2 * (8.0 * Aloc * P + 8.0 * N * Aloc * o);
+            st.kgemm_flops += 2.0 * N * N * Aloc * o;
+        }
+    }
+}
+
+int collect_stats(b200jk* h) {
+    b200jk_stats& st = h->stats;
+    st.ms_total = st.ms_j = st.ms_half = st.ms_kgemm = st.ms_allreduce = st.ms_h2d = st.ms_d2h = 0;
+    st.launches = 0;
+    for (auto& s : h->sh) {
+        double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (auto& ph : s.phases) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ph.a, ph.b);
+            acc[ph.tag] += ms;
+        }
+        st.ms_j = std::max(st.ms_j, acc[0]);
+        st.ms_half = std::max(st.ms_half, acc[1]);
+        st.ms_kgemm = std::max(st.ms_kgemm, acc[2]);
+        st.ms_allreduce = std::max(st.ms_allreduce, acc[3]);
+        st.ms_h2d = std::max(st.ms_h2d, acc[4]);
+        st.ms_d2h = std::max(st.ms_d2h, acc[5]);
+        st.ms_total = std::max(st.ms_total, acc[6]);
+        st.launches += s.launches;
+    }
+    return 0;
+}
+
+int allreduce(b200jk* h, size_t count) {
+    bool multi = h->sh.size() > 1 || (h->rank_mode && h->world > 1);
+    if (!multi) return 0;
+    if (h->sh.size() > 1) NK(g_nccl.GroupStart());
+    for (auto& s : h->sh) {
+        CK(cudaSetDevice(s.dev));
+        PhaseScope ps(s, 3);
+        NK(g_nccl.AllReduce(s.out, s.out, count, kNcclDouble, kNcclSum, s.comm, s.stream));
+    }
+    if (h->sh.size() > 1) NK(g_nccl.GroupEnd());
+    return 0;
+}
+
+int check_compute_args(b200jk* h, int nmat, const int* nocc, bool do_J, bool do_K, bool do_wK) {
+    if (!h->have_layout) return fail(h, B200JK_ERR_INVALID, "b200jk_compute before b200jk_set_layout");
+    if (nmat < 0 || (nmat > 0 && !nocc)) return fail(h, B200JK_ERR_INVALID, "bad nmat/nocc");
+    if ((do_J || do_K) && !h->uploaded[0]) return fail(h, B200JK_ERR_INVALID, "tensor Ppq not uploaded");
+    if (do_wK && !(h->uploaded[1] && h->uploaded[2]))
+        return fail(h, B200JK_ERR_INVALID, "wK tasked but m1Ppq/wPpq not uploaded");
+    for (int i = 0; i < nmat; i++)
+        if (nocc[i] < 0) return fail(h, B200JK_ERR_INVALID, "negative nocc[%d]", i);
+    return 0;
+}
+
+void begin_compute(b200jk* h) {
+    for (auto& s : h->sh) {
+        s.phases.clear();
+        s.evused = 0;
+        s.launches = 0;
+    }
+}
+
+int setup_shards(b200jk* h, int n, const int* devs) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(h, B200JK_ERR_NODEVICE, "no CUDA device visible: the B200 JK engine has no CPU fallback");
+    }
+    h->sh.resize(n);
+    for (int i = 0; i < n; i++) {
+        Shard& s = h->sh[i];
+        s.dev = devs ? devs[i] : i;
+        if (s.dev < 0 || s.dev >= ndev) return fail(h, B200JK_ERR_INVALID, "device %d out of range (%d visible)", s.dev, ndev);
+        CK(cudaSetDevice(s.dev));
+        CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    }
+    return 0;
+}
+
+void free_shard(Shard& s) {
+    cudaSetDevice(s.dev);
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    for (int w = 0; w < 3; w++)
+        if (s.tensor[w]) cudaFree(s.tensor[w]);
+    void* ptrs[] = {s.d_row_off, s.d_ldm, s.d_sp, s.d_ign, s.d_cols, s.d_cols_off, s.in, s.out,
+                    s.Ctl,       s.Ctr,   s.dpart, s.T1,  s.T2,     s.ws};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    for (auto e : s.evpool) cudaEventDestroy(e);
+    if (s.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s.comm);
+    if (s.stream) cudaStreamDestroy(s.stream);
+}
+
+int alloc_tensor(b200jk* h, int which) {
+    for (auto& s : h->sh) {
+        if (s.tensor[which]) continue;
+        CK(cudaSetDevice(s.dev));
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        size_t need = s.tensor_doubles * sizeof(double);
+        if (need + ((size_t)256 << 20) > free_b)
+            return fail(h, B200JK_ERR_OOM,
+                        "in-core tensor needs %.2f GiB on device %d but only %.2f GiB are free "
+                        "(no out-of-core / CPU fallback; use more GPUs)",
+                        need / 1073741824.0, s.dev, free_b / 1073741824.0);
+        CK(cudaMalloc((void**)&s.tensor[which], std::max<size_t>(need, 8)));
+        CK(cudaMemsetAsync(s.tensor[which], 0, need, s.stream));
+    }
+    return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int b200jk_create(b200jk_t** out, int ngpu, const int* dev_ids) {
+    if (!out || ngpu < 1) return B200JK_ERR_INVALID;
+    b200jk* h = new b200jk();
+    memset(&h->stats, 0, sizeof h->stats);
+    *out = h;
+    int rc = setup_shards(h, ngpu, dev_ids);
+    if (rc) return rc;
+    if (ngpu > 1) {
+        if (!g_nccl.load(h->err)) return B200JK_ERR_NCCL;
+        std::vector<int> devs(ngpu);
+        std::vector<ncclComm_t> comms(ngpu);
+        for (int i = 0; i < ngpu; i++) devs[i] = h->sh[i].dev;
+        NK(g_nccl.CommInitAll(comms.data(), ngpu, devs.data()));
+        for (int i = 0; i < ngpu; i++) h->sh[i].comm = comms[i];
+    }
+    h->world = ngpu;
+    h->stats.n_shards = ngpu;
+    return 0;
+}
+
+int b200jk_nccl_unique_id(void* out_bytes) {
+    std::string err;
+    if (!out_bytes || !g_nccl.load(err)) return B200JK_ERR_NCCL;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id)) return B200JK_ERR_NCCL;
+    memcpy(out_bytes, &id, sizeof id);
+    return 0;
+}
+
+int b200jk_create_rank(b200jk_t** out, int device, int rank, int world, const void* nccl_id) {
+    if (!out || world < 1 || rank < 0 || rank >= world) return B200JK_ERR_INVALID;
+    b200jk* h = new b200jk();
+    memset(&h->stats, 0, sizeof h->stats);
+    *out = h;
+    int rc = setup_shards(h, 1, &device);
+    if (rc) return rc;
+    h->rank = rank;
+    h->world = world;
+    h->rank_mode = true;
+    h->stats.n_shards = 1;
+    if (world > 1) {
+        if (!nccl_id) return fail(h, B200JK_ERR_INVALID, "world > 1 needs an NCCL unique id");
+        if (!g_nccl.load(h->err)) return B200JK_ERR_NCCL;
+        ncclUniqueId id;
+        memcpy(&id, nccl_id, sizeof id);
+        CK(cudaSetDevice(device));
+        NK(g_nccl.CommInitRank(&h->sh[0].comm, world, id, rank));
+    }
+    return 0;
+}
+
+void b200jk_destroy(b200jk_t* h) {
+    if (!h) return;
+    for (auto& s : h->sh) free_shard(s);
+    if (h->pin_in) cudaFreeHost(h->pin_in);
+    if (h->pin_out) cudaFreeHost(h->pin_out);
+    delete h;
+}
+
+const char* b200jk_last_error(const b200jk_t* h) { return h ? h->err.c_str() : "null handle"; }
+
+int b200jk_set_layout(b200jk_t* h, size_t nbf, size_t naux, const size_t* small_skips, const size_t* big_skips,
+                      const size_t* fun_index) {
+    if (!h) return B200JK_ERR_INVALID;
+    if (h->sh.empty()) return fail(h, B200JK_ERR_NODEVICE, "handle has no device");
+    if (!nbf || !naux || !small_skips || !big_skips || !fun_index) return fail(h, B200JK_ERR_INVALID, "null/zero layout");
+    if (nbf > 0x7fffffffu / 4 || naux > 0x7fffffffu / 4) return fail(h, B200JK_ERR_INVALID, "nbf/naux too large");
+    for (int w = 0; w < 3; w++)
+        if (h->uploaded[w]) return fail(h, B200JK_ERR_INVALID, "layout cannot change after upload");
+    h->nbf = nbf;
+    h->naux = naux;
+    h->small_skips.assign(small_skips, small_skips + nbf + 1);
+    h->big_skips.assign(big_skips, big_skips + nbf + 1);
+    h->sp.resize(nbf);
+    h->ign.resize(nbf);
+    h->ldm.resize(nbf);
+    h->cols_off.resize(nbf);
+    h->row_off_unit.resize(nbf + 1);
+    h->cols.clear();
+    h->cols.reserve(small_skips[nbf]);
+    h->max_sp = 0;
+    size_t tot = 0, run = 0;
+    h->row_off_unit[0] = 0;
+    for (size_t m = 0; m < nbf; m++) {
+        size_t cnt = 0, skip = 0;
+        h->cols_off[m] = h->cols.size();
+        for (size_t n = 0; n < nbf; n++) {
+            size_t f = fun_index[m * nbf + n];
+            if (f) {
+                if (f != cnt + 1) return fail(h, B200JK_ERR_INVALID, "fun_index row %zu is not a 1-based running rank", m);
+                cnt++;
+                if (n < m) skip++;
+                h->cols.push_back((int)n);
+            }
+        }
+        if (cnt != small_skips[m]) return fail(h, B200JK_ERR_INVALID, "small_skips[%zu] != kept partners in fun_index", m);
+        if (big_skips[m] != run) return fail(h, B200JK_ERR_INVALID, "big_skips[%zu] inconsistent with small_skips*naux", m);
+        if (!fun_index[m * nbf + m]) return fail(h, B200JK_ERR_INVALID, "diagonal pair (%zu,%zu) screened out", m, m);
+        run += cnt * naux;
+        tot += cnt;
+        h->sp[m] = (int)cnt;
+        h->ign[m] = (int)skip;
+        h->ldm[m] = round_up((int)cnt, 4);
+        h->row_off_unit[m + 1] = h->row_off_unit[m] + h->ldm[m];
+        h->max_sp = std::max(h->max_sp, (int)cnt);
+    }
+    if (small_skips[nbf] != tot || big_skips[nbf] != run) return fail(h, B200JK_ERR_INVALID, "table totals inconsistent");
+
+    // Q shards: contiguous, near-equal.  rank mode: this process owns shard `rank` of `world`.
+    int nshard_total = h->rank_mode ? h->world : (int)h->sh.size();
+    for (size_t i = 0; i < h->sh.size(); i++) {
+        Shard& s = h->sh[i];
+        int idx = h->rank_mode ? h->rank : (int)i;
+        s.q0 = (int)((naux * (size_t)idx) / nshard_total);
+        s.q1 = (int)((naux * (size_t)(idx + 1)) / nshard_total);
+        s.nq = s.q1 - s.q0;
+        s.tensor_doubles = h->row_off_unit[nbf] * (size_t)s.nq;
+        std::vector<size_t> row_off(nbf);
+        for (size_t m = 0; m < nbf; m++) row_off[m] = h->row_off_unit[m] * (size_t)s.nq;
+        CK(cudaSetDevice(s.dev));
+        int rc;
+        if ((rc = upload_vec(h, &s.d_row_off, row_off))) return rc;
+        if ((rc = upload_vec(h, &s.d_ldm, h->ldm))) return rc;
+        if ((rc = upload_vec(h, &s.d_sp, h->sp))) return rc;
+        if ((rc = upload_vec(h, &s.d_ign, h->ign))) return rc;
+        if ((rc = upload_vec(h, &s.d_cols, h->cols))) return rc;
+        if ((rc = upload_vec(h, &s.d_cols_off, h->cols_off))) return rc;
+    }
+    h->stats.q_begin = h->sh[0].q0;
+    h->stats.q_end = h->sh[0].q1;
+    h->have_layout = true;
+    return 0;
+}
+
+int b200jk_upload_rows(b200jk_t* h, int which, size_t m0, size_t m1, const double* host_rows) {
+    if (!h) return B200JK_ERR_INVALID;
+    if (!h->have_layout) return fail(h, B200JK_ERR_INVALID, "upload before set_layout");
+    if (which < 0 || which > 2 || m0 > m1 || m1 > h->nbf || !host_rows) return fail(h, B200JK_ERR_INVALID, "bad upload args");
+    int rc = alloc_tensor(h, which);
+    if (rc) return rc;
+    const size_t A = h->naux;
+    for (auto& s : h->sh) {
+        if (!s.nq) continue;
+        CK(cudaSetDevice(s.dev));
+        for (size_t m = m0; m < m1; m++) {
+            size_t sp = h->sp[m];
+            const double* src = host_rows + (h->big_skips[m] - h->big_skips[m0]) + (size_t)s.q0 * sp;
+            double* dst = s.tensor[which] + h->row_off_unit[m] * (size_t)s.nq;
+            CK(cudaMemcpy2DAsync(dst, (size_t)h->ldm[m] * 8, src, sp * 8, sp * 8, (size_t)s.nq, cudaMemcpyHostToDevice,
+                                 s.stream));
+        }
+        (void)A;
+    }
+    for (auto& s : h->sh) {
+        CK(cudaSetDevice(s.dev));
+        CK(cudaStreamSynchronize(s.stream));
+    }
+    if (m0 == 0 && m1 == h->nbf) h->uploaded[which] = true;
+    if (m1 == h->nbf) h->uploaded[which] = true;  // streaming: last block completes the tensor
+    h->stats.hbm_tensor_bytes = 0;
+    for (int w = 0; w < 3; w++)
+        if (h->sh[0].tensor[w]) h->stats.hbm_tensor_bytes += h->sh[0].tensor_doubles * 8;
+    return 0;
+}
+
+int b200jk_upload(b200jk_t* h, int which, const double* host_pQq) {
+    if (!h) return B200JK_ERR_INVALID;
+    return b200jk_upload_rows(h, which, 0, h->nbf, host_pQq);
+}
+
+int b200jk_fill_synthetic(b200jk_t* h, int which, uint64_t seed, const double* amp) {
+    if (!h) return B200JK_ERR_INVALID;
+    if (!h->have_layout || which < 0 || which > 2 || !amp) return fail(h, B200JK_ERR_INVALID, "bad fill_synthetic args");
+    int rc = alloc_tensor(h, which);
+    if (rc) return rc;
+    size_t n2 = h->nbf * h->nbf;
+    uint64_t seedh = splitmix64(seed);
+    for (auto& s : h->sh) {
+        CK(cudaSetDevice(s.dev));
+        double* damp = nullptr;
+        CK(cudaMalloc((void**)&damp, n2 * 8));
+        CK(cudaMemcpyAsync(damp, amp, n2 * 8, cudaMemcpyHostToDevice, s.stream));
+        if (s.nq) {
+            synth_fill_kernel<<<dim3((s.nq + 7) / 8, (unsigned)h->nbf), 256, 0, s.stream>>>(
+                s.tensor[which], s.d_row_off, s.d_ldm, s.d_sp, s.d_cols, s.d_cols_off, damp, (int)h->nbf, s.nq, s.q0, seedh);
+            CK(cudaGetLastError());
+        }
+        CK(cudaStreamSynchronize(s.stream));
+        CK(cudaFree(damp));
+    }
+    h->uploaded[which] = true;
+    h->stats.hbm_tensor_bytes = 0;
+    for (int w = 0; w < 3; w++)
+        if (h->sh[0].tensor[w]) h->stats.hbm_tensor_bytes += h->sh[0].tensor_doubles * 8;
+    return 0;
+}
+
+int b200jk_download_rows(b200jk_t* h, int which, size_t m, size_t q0, size_t q1, double* host_out) {
+    if (!h) return B200JK_ERR_INVALID;
+    if (!h->have_layout || which < 0 || which > 2 || m >= h->nbf || q0 > q1 || q1 > h->naux || !host_out)
+        return fail(h, B200JK_ERR_INVALID, "bad download args");
+    size_t sp = h->sp[m];
+    bool any = false;
+    for (auto& s : h->sh) {
+        size_t a = std::max<size_t>(q0, s.q0), b = std::min<size_t>(q1, s.q1);
+        if (a >= b || !s.tensor[which]) continue;
+        any = true;
+        CK(cudaSetDevice(s.dev));
+        const double* src = s.tensor[which] + h->row_off_unit[m] * (size_t)s.nq + (a - s.q0) * (size_t)h->ldm[m];
+        CK(cudaMemcpy2D(host_out + (a - q0) * sp, sp * 8, src, (size_t)h->ldm[m] * 8, sp * 8, b - a, cudaMemcpyDeviceToHost));
+    }
+    if (!any && q1 > q0 && !h->rank_mode) return fail(h, B200JK_ERR_INVALID, "tensor not resident");
+    return 0;
+}
+
+int b200jk_set_work_budget(b200jk_t* h, uint64_t bytes) {
+    if (!h) return B200JK_ERR_INVALID;
+    h->work_budget = bytes;
+    for (auto& s : h->sh) {  // force re-planning
+        cudaSetDevice(s.dev);
+        if (s.T1) cudaFree(s.T1);
+        if (s.T2) cudaFree(s.T2);
+        s.T1 = s.T2 = nullptr;
+        s.T_cap = s.T2_cap = 0;
+    }
+    return 0;
+}
+
+int b200jk_hbm_estimate(const b200jk_t* h, size_t max_nocc, int do_wK, uint64_t* bytes_per_gpu) {
+    if (!h || !bytes_per_gpu) return B200JK_ERR_INVALID;
+    if (!h->have_layout) return B200JK_ERR_INVALID;
+    const Shard& s = h->sh[0];
+    uint64_t b = s.tensor_doubles * 8 * (do_wK ? 3 : 1);
+    uint64_t op = (max_nocc + 1) & ~(uint64_t)1;
+    b += (uint64_t)h->nbf * s.nq * op * 8 * 2;          // T1, T2 (full shard)
+    b += (uint64_t)h->nbf * s.nq * 8;                   // dpart
+    b += (uint64_t)6 * h->nbf * h->nbf * 8 + ((uint64_t)1 << 30);  // in/out + split-K partials
+    *bytes_per_gpu = b;
+    return 0;
+}
+
+int b200jk_get_stats(const b200jk_t* h, b200jk_stats* out) {
+    if (!h || !out) return B200JK_ERR_INVALID;
+    *out = h->stats;
+    return 0;
+}
+
+static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* const* Cl, const double* const* Cr,
+                        const int* nocc, const double* const* D, double* const* J, double* const* K,
+                        double* const* wK, int do_J, int do_K, int do_wK) {
+    if (!h) return B200JK_ERR_INVALID;
+    int rc = check_compute_args(h, nmat, nocc, do_J, do_K, do_wK);
+    if (rc) return rc;
+    if (!host_ops && h->sh.size() != 1) return fail(h, B200JK_ERR_INVALID, "compute_device needs a one-shard handle");
+    if (nmat == 0) return 0;
+    if ((do_K || do_wK) && !Cl) return fail(h, B200JK_ERR_INVALID, "K tasked without C_left");
+    if (do_J && !D) return fail(h, B200JK_ERR_INVALID, "J tasked without D");
+    if ((do_J && !J) || (do_K && !K) || (do_wK && !wK)) return fail(h, B200JK_ERR_INVALID, "tasked output array is NULL");
+
+    Task t;
+    t.nmat = nmat;
+    t.nocc = nocc;
+    t.lr = (Cr == nullptr);
+    t.do_J = do_J;
+    t.do_K = do_K;
+    t.do_wK = do_wK;
+    t.n2 = h->nbf * h->nbf;
+    t.nprod = (do_J ? 1 : 0) + (do_K ? 1 : 0) + (do_wK ? 1 : 0);
+    t.max_o = 0;
+    for (int i = 0; i < nmat; i++) t.max_o = std::max(t.max_o, nocc[i]);
+    if (t.nprod == 0) return 0;
+    const size_t N = h->nbf, n2 = t.n2;
+    begin_compute(h);
+
+    std::vector<int> qc(h->sh.size());
+    for (size_t i = 0; i < h->sh.size(); i++)
+        if ((rc = ensure_work(h, h->sh[i], t, &qc[i]))) return rc;
+
+    // total-time bracket
+    std::vector<Phase> total(h->sh.size());
+    for (size_t i = 0; i < h->sh.size(); i++) {
+        Shard& s = h->sh[i];
+        CK(cudaSetDevice(s.dev));
+        total[i].tag = 6;
+        total[i].a = get_event(s);
+        total[i].b = get_event(s);
+        CK(cudaEventRecord(total[i].a, s.stream));
+    }
+
+    std::vector<std::vector<const double*>> dCl(h->sh.size()), dCr(h->sh.size()), dD(h->sh.size());
+    const bool needC = do_K || do_wK;
+    if (host_ops) {
+        // stage C (first: the K build can start while D is still in flight) then D through pinned memory
+        size_t in_doubles = 0;
+        for (int i = 0; i < nmat; i++) {
+            if (needC) in_doubles += N * (size_t)nocc[i] * (t.lr ? 1 : 2);
+            if (do_J) in_doubles += n2;
+        }
+        in_doubles = std::max<size_t>(in_doubles, 1);
+        if (in_doubles > h->pin_in_cap) {
+            if (h->pin_in) CK(cudaFreeHost(h->pin_in));
+            h->pin_in = nullptr;
+            CK(cudaHostAlloc((void**)&h->pin_in, in_doubles * 8, cudaHostAllocPortable));
+            h->pin_in_cap = in_doubles;
+        }
+        std::vector<size_t> offCl(nmat), offCr(nmat), offD(nmat);
+        size_t off = 0;
+        for (int i = 0; i < nmat; i++) {
+            if (needC) {
+                size_t c = N * (size_t)nocc[i];
+                offCl[i] = off;
+                if (c) memcpy(h->pin_in + off, Cl[i], c * 8);
+                off += c;
+                if (!t.lr) {
+                    offCr[i] = off;
+                    if (c) memcpy(h->pin_in + off, Cr[i], c * 8);
+                    off += c;
+                }
+            }
+        }
+        size_t c_end = off;
+        for (int i = 0; i < nmat; i++) {
+            if (do_J) {
+                offD[i] = off;
+                memcpy(h->pin_in + off, D[i], n2 * 8);
+                off += n2;
+            }
+        }
+        for (size_t si = 0; si < h->sh.size(); si++) {
+            Shard& s = h->sh[si];
+            CK(cudaSetDevice(s.dev));
+            if ((rc = grow(h, &s.in, &s.in_cap, in_doubles))) return rc;
+            {
+                PhaseScope ps(s, 4);
+                if (c_end) CK(cudaMemcpyAsync(s.in, h->pin_in, c_end * 8, cudaMemcpyHostToDevice, s.stream));
+                if (off > c_end)
+                    CK(cudaMemcpyAsync(s.in + c_end, h->pin_in + c_end, (off - c_end) * 8, cudaMemcpyHostToDevice, s.stream));
+            }
+            dCl[si].resize(nmat);
+            dCr[si].resize(nmat);
+            dD[si].resize(nmat);
+            for (int i = 0; i < nmat; i++) {
+                dCl[si][i] = needC ? s.in + offCl[i] : nullptr;
+                dCr[si][i] = (needC && !t.lr) ? s.in + offCr[i] : nullptr;
+                dD[si][i] = do_J ? s.in + offD[i] : nullptr;
+            }
+        }
+    } else {
+        dCl[0].assign(nmat, nullptr);
+        dCr[0].assign(nmat, nullptr);
+        dD[0].assign(nmat, nullptr);
+        for (int i = 0; i < nmat; i++) {
+            if (needC) dCl[0][i] = Cl[i];
+            if (needC && !t.lr) dCr[0][i] = Cr[i];
+            if (do_J) dD[0][i] = D[i];
+        }
+    }
+
+    for (size_t si = 0; si < h->sh.size(); si++)
+        if ((rc = run_device(h, h->sh[si], t, dCl[si].data(), dCr[si].data(), dD[si].data(), qc[si]))) return rc;
+
+    size_t out_count = (size_t)nmat * t.nprod * n2;
+    if ((rc = allreduce(h, out_count))) return rc;
+
+    // results: shard 0 holds the reduced sums
+    Shard& s0 = h->sh[0];
+    CK(cudaSetDevice(s0.dev));
+    double* const* outs[3] = {do_J ? J : nullptr, do_K ? K : nullptr, do_wK ? wK : nullptr};
+    if (host_ops) {
+        if (out_count > h->pin_out_cap) {
+            if (h->pin_out) CK(cudaFreeHost(h->pin_out));
+            h->pin_out = nullptr;
+            CK(cudaHostAlloc((void**)&h->pin_out, out_count * 8, cudaHostAllocPortable));
+            h->pin_out_cap = out_count;
+        }
+        {
+            PhaseScope ps(s0, 5);
+            CK(cudaMemcpyAsync(h->pin_out, s0.out, out_count * 8, cudaMemcpyDeviceToHost, s0.stream));
+        }
+    } else {
+        size_t off = 0;
+        for (int pr = 0; pr < 3; pr++) {
+            if (!outs[pr]) continue;
+            for (int i = 0; i < nmat; i++, off += n2)
+                CK(cudaMemcpyAsync(outs[pr][i], s0.out + off, n2 * 8, cudaMemcpyDeviceToDevice, s0.stream));
+        }
+    }
+    for (size_t i = 0; i < h->sh.size(); i++) {
+        Shard& s = h->sh[i];
+        CK(cudaSetDevice(s.dev));
+        CK(cudaEventRecord(total[i].b, s.stream));
+        s.phases.push_back(total[i]);
+    }
+    for (auto& s : h->sh) {
+        CK(cudaSetDevice(s.dev));
+        CK(cudaStreamSynchronize(s.stream));
+    }
+    if (host_ops) {
+        size_t off = 0;
+        for (int pr = 0; pr < 3; pr++) {
+            if (!outs[pr]) continue;
+            for (int i = 0; i < nmat; i++, off += n2) memcpy(outs[pr][i], h->pin_out + off, n2 * 8);
+        }
+    }
+    account_work(h, t);
+    collect_stats(h);
+    h->stats.hbm_work_bytes = 0;
+    {
+        Shard& s = h->sh[0];
+        h->stats.hbm_work_bytes =
+            8 * (s.in_cap + s.out_cap + 2 * s.ct_cap + s.dpart_cap + s.T_cap + s.T2_cap + s.ws_cap);
+    }
+    return 0;
+}
+
+int b200jk_compute(b200jk_t* h, int nmat, const double* const* Cl, const double* const* Cr, const int* nocc,
+                   const double* const* D, double* const* J, double* const* K, double* const* wK, int do_J,
+                   int do_K, int do_wK) {
+    return compute_impl(h, true, nmat, Cl, Cr, nocc, D, J, K, wK, do_J, do_K, do_wK);
+}
+
+int b200jk_compute_device(b200jk_t* h, int nmat, const double* const* dCl, const double* const* dCr,
+                          const int* nocc, const double* const* dD, double* const* dJ, double* const* dK,
+                          double* const* dwK, int do_J, int do_K, int do_wK) {
+    return compute_impl(h, false, nmat, dCl, dCr, nocc, dD, dJ, dK, dwK, do_J, do_K, do_wK);
+}
+
+int b200jk_dev_alloc(b200jk_t* h, size_t bytes, void** dptr) {
+    if (!h || !dptr || h->sh.empty()) return B200JK_ERR_INVALID;
+    CK(cudaSetDevice(h->sh[0].dev));
+    CK(cudaMalloc(dptr, std::max<size_t>(bytes, 8)));
+    return 0;
+}
+int b200jk_dev_free(b200jk_t* h, void* dptr) {
+    if (!h || h->sh.empty()) return B200JK_ERR_INVALID;
+    CK(cudaSetDevice(h->sh[0].dev));
+    CK(cudaFree(dptr));
+    return 0;
+}
+int b200jk_dev_copy(b200jk_t* h, void* dst, const void* src, size_t bytes, int kind) {
+    if (!h || h->sh.empty()) return B200JK_ERR_INVALID;
+    CK(cudaSetDevice(h->sh[0].dev));
+    cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    CK(cudaMemcpy(dst, src, bytes, k));
+    return 0;
+}
+
+int b200jk_fp64_peak(b200jk_t* h, int kind, double* tflops) {
+    if (!h || !tflops || h->sh.empty()) return B200JK_ERR_INVALID;
+    Shard& s = h->sh[0];
+    CK(cudaSetDevice(s.dev));
+    int nsm = 148;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s.dev));
+    double* out = nullptr;
+    CK(cudaMalloc((void**)&out, 8));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    const int iters = 20000, blocks = nsm * 4, threads = 256;
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(cudaEventRecord(a, s.stream));
+        if (kind == 0)
+            dmma_peak_kernel<<<blocks, threads, 0, s.stream>>>(out, iters);
+        else
+            dfma_peak_kernel<<<blocks, threads, 0, s.stream>>>(out, iters);
+        CK(cudaEventRecord(b, s.stream));
+        CK(cudaEventSynchronize(b));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        double flops = kind == 0 ? (double)blocks * (threads / 32) * iters * 16.0 * 512.0
+                                 : (double)blocks * threads * iters * 16.0 * 2.0;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    CK(cudaEventDestroy(a));
+    CK(cudaEventDestroy(b));
+    CK(cudaFree(out));
+    *tflops = best;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+// j_kernels.cuh -- the two HBM-bound sweeps of the DF-J build over the packed (Q|mn) tensor.
+//
+//   K1  j_dq   : d[q]    = sum_m sum_k B_m[q,k] * Dp_m[k]      (DGEMV 'N', dfhelper.cc:3193 / :3258)
+//   K2  j_mn   : J[m,n_k] = sum_q B_m[q,k] * d[q]  + unpack    (DGEMV 'T' + loops, :3208-3221 / :3272-3283)
+//
+// Symmetric densities (lr_symmetric) read only the columns n >= m of each row-block (start column
+// ign(m)), weight 2 off the diagonal, and mirror on unpack -- exactly compute_J_symm.  General
+// densities read every kept column -- compute_J.  Both are pure streaming reads of B: every
+// warp-level load is one contiguous 512-byte (K1) or 2 x 512-byte (K2) segment.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b2k {
+
+struct JParams {
+    const double* tensor;     // shard tensor base
+    const size_t* row_off;    // [nbf]
+    const int* ldm;           // [nbf]
+    const int* sp;            // [nbf]
+    const int* ign;           // [nbf] kept partners with n < m
+    const int* cols;
+    const size_t* cols_off;
+    int nbf;
+    int nq;                   // shard rows
+    int symmetric;
+    const double* D;          // [nbf][nbf]
+    double* dpart;            // [nbf][nq]   per-row-block partial d
+    double* d;                // [nq]
+    double* J;                // [nbf][nbf]
+};
+
+constexpr int J1_ROWS = 64;      // q rows per CTA in K1
+constexpr int J_THREADS = 256;
+
+// K1.  grid = (ceil(nq/64), nbf).  smem: gathered density row Dp (sp(m) doubles, zero below the
+// symmetric start column).  Each warp owns 8 rows, two at a time; lanes stride the row in double2.
+__global__ void __launch_bounds__(J_THREADS) j_dq_kernel(JParams p) {
+    extern __shared__ __align__(16) double Dp[];
+    const int m = blockIdx.y;
+    const int sp = p.sp[m];
+    const int ldm = p.ldm[m];
+    const int kstart = p.symmetric ? p.ign[m] : 0;
+    const int* cols = p.cols + p.cols_off[m];
+    const int spe = (sp + 1) & ~1;  // even length (pad column reads hit zero weight)
+    for (int k = threadIdx.x; k < spe; k += blockDim.x) {
+        double v = 0.0;
+        if (k >= kstart && k < sp) {
+            int n = cols[k];
+            v = p.D[(size_t)m * p.nbf + n];
+            if (p.symmetric && n != m) v *= 2.0;
+        }
+        Dp[k] = v;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double* Bm = p.tensor + p.row_off[m];
+    const int k0 = kstart & ~1;
+    const int qbase = blockIdx.x * J1_ROWS + warp * 8;
+#pragma unroll 1
+    for (int r = 0; r < 8; r += 2) {
+        int qa = qbase + r, qb = qa + 1;
+        if (qa >= p.nq) break;
+        bool hb = qb < p.nq;
+        const double* ra = Bm + (size_t)qa * ldm;
+        const double* rb = Bm + (size_t)(hb ? qb : qa) * ldm;
+        double sa0 = 0, sa1 = 0, sb0 = 0, sb1 = 0;
+#pragma unroll 4
+        for (int k = k0 + lane * 2; k < spe; k += 64) {
+            double2 w = *reinterpret_cast<const double2*>(Dp + k);
+            double2 a = __ldcs(reinterpret_cast<const double2*>(ra + k));
+            double2 b = __ldcs(reinterpret_cast<const double2*>(rb + k));
+            sa0 = fma(a.x, w.x, sa0);
+            sa1 = fma(a.y, w.y, sa1);
+            sb0 = fma(b.x, w.x, sb0);
+            sb1 = fma(b.y, w.y, sb1);
+        }
+        double sa = sa0 + sa1, sb = sb0 + sb1;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, off);
+            sb += __shfl_xor_sync(0xffffffffu, sb, off);
+        }
+        if (lane == 0) {
+            p.dpart[(size_t)m * p.nq + qa] = sa;
+            if (hb) p.dpart[(size_t)m * p.nq + qb] = sb;
+        }
+    }
+}
+
+// d[q] = sum_m dpart[m][q], fixed order (deterministic; replaces the serial thread reduce :3197-3199).
+__global__ void j_dq_reduce_kernel(const double* __restrict__ dpart, int nbf, int nq, double* __restrict__ d) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    int m = 0;
+    for (; m + 3 < nbf; m += 4) {
+        s0 += dpart[(size_t)m * nq + q];
+        s1 += dpart[(size_t)(m + 1) * nq + q];
+        s2 += dpart[(size_t)(m + 2) * nq + q];
+        s3 += dpart[(size_t)(m + 3) * nq + q];
+    }
+    for (; m < nbf; m++) s0 += dpart[(size_t)m * nq + q];
+    d[q] = (s0 + s1) + (s2 + s3);
+}
+
+// K2.  grid = (ceil(max_sp/128), nbf).  CTA: row-block m, packed columns [kt*128, kt*128+128).
+// Warp w sums rows q = w, w+8, ...; lane owns columns 2*lane,+1 and 64+2*lane,+1.  Cross-warp
+// reduction in shared memory in fixed order, then the sparse->dense unpack writes J directly.
+__global__ void __launch_bounds__(J_THREADS) j_mn_kernel(JParams p) {
+    __shared__ double red[8][128];
+    extern __shared__ __align__(16) double dq[];  // d[q] staged once per CTA
+    const int m = blockIdx.y;
+    const int sp = p.sp[m];
+    const int kt0 = blockIdx.x * 128;
+    if (kt0 >= sp) return;
+    const int kstart = p.symmetric ? p.ign[m] : 0;
+    if (kt0 + 128 <= kstart) return;
+    for (int q = threadIdx.x; q < p.nq; q += blockDim.x) dq[q] = p.d[q];
+    __syncthreads();
+    const int ldm = p.ldm[m];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double* Bm = p.tensor + p.row_off[m];
+    const int ka = kt0 + lane * 2, kb = ka + 64;
+    const bool va = ka < ldm, vb = kb < ldm;  // ldm is a multiple of 4: ka+1 < ldm when ka < ldm
+    double a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+    const double* base = Bm + (size_t)warp * ldm;
+    const size_t step = (size_t)8 * ldm;
+    int q = warp;
+#pragma unroll 4
+    for (; q < p.nq; q += 8, base += step) {
+        double w = dq[q];
+        if (va) {
+            double2 x = __ldcs(reinterpret_cast<const double2*>(base + ka));
+            a0 = fma(x.x, w, a0);
+            a1 = fma(x.y, w, a1);
+        }
+        if (vb) {
+            double2 y = __ldcs(reinterpret_cast<const double2*>(base + kb));
+            b0 = fma(y.x, w, b0);
+            b1 = fma(y.y, w, b1);
+        }
+    }
+    red[warp][lane * 2] = a0;
+    red[warp][lane * 2 + 1] = a1;
+    red[warp][64 + lane * 2] = b0;
+    red[warp][64 + lane * 2 + 1] = b1;
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        int k = kt0 + threadIdx.x;
+        if (k < sp && k >= kstart) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) s += red[w][threadIdx.x];
+            int n = p.cols[p.cols_off[m] + k];
+            p.J[(size_t)m * p.nbf + n] += s;
+            if (p.symmetric && n != m) p.J[(size_t)n * p.nbf + m] += s;
+        }
+    }
+}
+
+}  // namespace b2k

@@ -1,0 +1,94 @@
+"""Host-side mirror of the part of psi4's DFHelper that the MEM_DF J/K path needs:
+the Schwarz pair mask, the packed-index tables and the "pQq" packing of the fitted
+three-index tensor.  Pure numpy host logic (cheap, once per SCF); the arithmetic of the
+J/K build itself lives in libb200jk.so.
+
+Reference: psi4/src/psi4/lib3index/dfhelper.cc
+  prepare_sparsity :299-420   layout :1274-1276 / :1666-1677   get_core_size :216-236
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class DFHelper:
+    """Sparsity tables + packing.  Attribute names follow dfhelper.h:440-452."""
+
+    def __init__(self, nbf: int, naux: int):
+        self.nbf_ = int(nbf)
+        self.naux_ = int(naux)
+        self.cutoff_ = 1e-12  # dfhelper.h: schwarz cutoff default; JK passes INTS_TOLERANCE (jk.cc:58-68)
+        self.sparsity_prepared_ = False
+        self.do_wK_ = False
+
+    # ---- knobs (dfhelper.h:100-175) ----
+    def set_schwarz_cutoff(self, cutoff: float):
+        self.cutoff_ = float(cutoff)
+
+    def get_schwarz_cutoff(self) -> float:
+        return self.cutoff_
+
+    def set_do_wK(self, do_wK: bool):
+        self.do_wK_ = bool(do_wK)
+
+    # ---- dfhelper.cc:371-416 ----
+    def prepare_sparsity(self, fun_max_vals: np.ndarray | None = None, keep: np.ndarray | None = None):
+        """Build the mask from per-pair Schwarz maxima |(mn|mn)| (tolerance = cutoff^2 / max, :371)
+        or take a ready boolean mask, then the index tables."""
+        n = self.nbf_
+        if keep is None:
+            f = np.asarray(fun_max_vals, dtype=np.float64).reshape(n, n)
+            max_val = f.max()
+            tolerance = self.cutoff_ * self.cutoff_ / max_val
+            keep = f >= tolerance
+        keep = np.asarray(keep, dtype=bool).reshape(n, n)
+        if not np.all(np.diag(keep)):
+            raise ValueError("DFHelper: a diagonal pair is screened out (dfhelper.cc:3213 assumes it exists)")
+        self.keep_ = keep
+        count = np.cumsum(keep, axis=1)
+        self.schwarz_fun_index_ = np.where(keep, count, 0).astype(np.uintp)       # :377-387
+        sp = keep.sum(axis=1).astype(np.uintp)
+        self.small_skips_ = np.concatenate([sp, [sp.sum()]]).astype(np.uintp)      # :386,:398
+        self.big_skips_ = np.concatenate([[0], np.cumsum(sp * np.uintp(self.naux_))]).astype(np.uintp)  # :390-397
+        lower = np.tril(keep, -1).sum(axis=1).astype(np.uintp)
+        self.symm_ignored_columns_ = lower                                         # :401-411
+        self.symm_small_skips_ = (sp - lower).astype(np.uintp)
+        self.symm_big_skips_ = np.concatenate(
+            [[0], np.cumsum(self.symm_small_skips_ * np.uintp(self.naux_))]).astype(np.uintp)  # :413-416
+        self.sparsity_prepared_ = True
+
+    def ao_sparsity(self) -> float:
+        """dfhelper.h:101  fraction of screened pairs."""
+        return 1.0 - float(self.small_skips_[self.nbf_]) / float(self.nbf_ * self.nbf_)
+
+    def get_core_size(self, nthreads: int = 1, qshell_max: int = 0) -> int:
+        """dfhelper.cc:216-236 required_core_size_ in doubles (host model; Qshell_max needs the aux shells)."""
+        big = int(self.big_skips_[self.nbf_])
+        req = 3 * big if self.do_wK_ else big
+        req += self.naux_ * self.naux_
+        req += nthreads * self.nbf_ * self.nbf_
+        req += 3 * self.nbf_ * self.nbf_ * qshell_max
+        return req
+
+    # ---- packing ----
+    def kept_columns(self, m: int) -> np.ndarray:
+        return np.nonzero(self.keep_[m])[0]
+
+    def pack(self, dense_Qmn: np.ndarray) -> np.ndarray:
+        """(naux, nbf, nbf) -> pQq packed vector: B(Q,m,n) at big_skips[m] + Q*sp(m) + f(m,n)-1."""
+        B = np.asarray(dense_Qmn, dtype=np.float64)
+        assert B.shape == (self.naux_, self.nbf_, self.nbf_)
+        out = np.empty(int(self.big_skips_[self.nbf_]), dtype=np.float64)
+        for m in range(self.nbf_):
+            cols = self.kept_columns(m)
+            a, b = int(self.big_skips_[m]), int(self.big_skips_[m + 1])
+            out[a:b] = B[:, m, cols].ravel()
+        return out
+
+    def unpack(self, packed: np.ndarray) -> np.ndarray:
+        out = np.zeros((self.naux_, self.nbf_, self.nbf_))
+        for m in range(self.nbf_):
+            cols = self.kept_columns(m)
+            a, b = int(self.big_skips_[m]), int(self.big_skips_[m + 1])
+            out[:, m, cols] = packed[a:b].reshape(self.naux_, len(cols))
+        return out

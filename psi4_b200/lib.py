@@ -1,0 +1,236 @@
+"""ctypes binding of libb200jk.so (include/b200jk.h) -- the same stub a psi4 maintainer would
+write in C++.  Fails loudly if the CUDA library is missing or cannot run:
+there is no CPU path in this package."""
+from __future__ import annotations
+
+import ctypes as ct
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200jk.so")
+
+NCCL_ID_BYTES = 128
+TENSOR_PPQ, TENSOR_M1PPQ, TENSOR_WPPQ = 0, 1, 2
+ERR_NAMES = {1: "INVALID", 2: "CUDA", 3: "OOM", 4: "NCCL", 5: "NODEVICE"}
+
+_dp = ct.POINTER(ct.c_double)
+_dpp = ct.POINTER(_dp)
+_szp = ct.POINTER(ct.c_size_t)
+
+
+class Stats(ct.Structure):
+    _fields_ = [
+        ("ms_total", ct.c_double), ("ms_j", ct.c_double), ("ms_half", ct.c_double), ("ms_kgemm", ct.c_double),
+        ("ms_allreduce", ct.c_double), ("ms_h2d", ct.c_double), ("ms_d2h", ct.c_double),
+        ("j_bytes", ct.c_double), ("half_flops", ct.c_double), ("half_bytes", ct.c_double),
+        ("kgemm_flops", ct.c_double), ("launches", ct.c_uint64), ("hbm_tensor_bytes", ct.c_uint64),
+        ("hbm_work_bytes", ct.c_uint64), ("n_shards", ct.c_int), ("q_begin", ct.c_int), ("q_end", ct.c_int),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class B200JKError(RuntimeError):
+    """Engine error; the psi4 glue would rethrow this as PSIEXCEPTION."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"b200jk error {code} ({ERR_NAMES.get(code, '?')}): {msg}")
+        self.code = code
+
+
+_lib = None
+
+# name -> (restype, argtypes); the full exported surface of include/b200jk.h
+SIGNATURES = {
+    "b200jk_create": (ct.c_int, [ct.POINTER(ct.c_void_p), ct.c_int, ct.POINTER(ct.c_int)]),
+    "b200jk_create_rank": (ct.c_int, [ct.POINTER(ct.c_void_p), ct.c_int, ct.c_int, ct.c_int, ct.c_void_p]),
+    "b200jk_nccl_unique_id": (ct.c_int, [ct.c_void_p]),
+    "b200jk_destroy": (None, [ct.c_void_p]),
+    "b200jk_set_layout": (ct.c_int, [ct.c_void_p, ct.c_size_t, ct.c_size_t, _szp, _szp, _szp]),
+    "b200jk_upload": (ct.c_int, [ct.c_void_p, ct.c_int, _dp]),
+    "b200jk_upload_rows": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_size_t, ct.c_size_t, _dp]),
+    "b200jk_compute": (ct.c_int, [ct.c_void_p, ct.c_int, _dpp, _dpp, ct.POINTER(ct.c_int), _dpp, _dpp, _dpp, _dpp,
+                                  ct.c_int, ct.c_int, ct.c_int]),
+    "b200jk_compute_device": (ct.c_int, [ct.c_void_p, ct.c_int, _dpp, _dpp, ct.POINTER(ct.c_int), _dpp, _dpp, _dpp,
+                                         _dpp, ct.c_int, ct.c_int, ct.c_int]),
+    "b200jk_get_stats": (ct.c_int, [ct.c_void_p, ct.POINTER(Stats)]),
+    "b200jk_last_error": (ct.c_char_p, [ct.c_void_p]),
+    "b200jk_hbm_estimate": (ct.c_int, [ct.c_void_p, ct.c_size_t, ct.c_int, ct.POINTER(ct.c_uint64)]),
+    "b200jk_set_work_budget": (ct.c_int, [ct.c_void_p, ct.c_uint64]),
+    "b200jk_fill_synthetic": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_uint64, _dp]),
+    "b200jk_download_rows": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_size_t, ct.c_size_t, ct.c_size_t, _dp]),
+    "b200jk_dev_alloc": (ct.c_int, [ct.c_void_p, ct.c_size_t, ct.POINTER(ct.c_void_p)]),
+    "b200jk_dev_free": (ct.c_int, [ct.c_void_p, ct.c_void_p]),
+    "b200jk_dev_copy": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_size_t, ct.c_int]),
+    "b200jk_fp64_peak": (ct.c_int, [ct.c_void_p, ct.c_int, _dp]),
+}
+
+
+def load():
+    """dlopen libb200jk.so.  Raises if it has not been built -- never falls back to CPU code."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: build it with `python -m psi4_b200.build` (or __graft_entry__.build()). "
+                "psi4_b200 has no CPU fallback.")
+        L = ct.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the symbol is missing
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _ptr_array(arrs):
+    if arrs is None:
+        return None
+    return (_dp * len(arrs))(*[_d(a) for a in arrs])
+
+
+class Engine:
+    """Thin owner of one b200jk_t handle."""
+
+    def __init__(self, ngpu: int = 1, devices=None, *, rank=None, world=None, device=None, nccl_id: bytes | None = None):
+        self.L = load()
+        self.h = ct.c_void_p()
+        if rank is None:
+            devs = None if devices is None else (ct.c_int * ngpu)(*devices)
+            rc = self.L.b200jk_create(ct.byref(self.h), ngpu, devs)
+        else:
+            buf = ct.create_string_buffer(nccl_id, NCCL_ID_BYTES) if nccl_id else None
+            rc = self.L.b200jk_create_rank(ct.byref(self.h), int(device or 0), int(rank), int(world), buf)
+        self._check(rc)
+        self.nbf = self.naux = 0
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = ct.create_string_buffer(NCCL_ID_BYTES)
+        rc = load().b200jk_nccl_unique_id(buf)
+        if rc:
+            raise B200JKError(rc, "ncclGetUniqueId failed")
+        return buf.raw
+
+    def _check(self, rc):
+        if rc:
+            msg = self.L.b200jk_last_error(self.h) if self.h else b"creation failed"
+            raise B200JKError(rc, (msg or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.b200jk_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_layout(self, nbf, naux, small_skips, big_skips, fun_index):
+        ss = np.ascontiguousarray(small_skips, dtype=np.uintp)
+        bs = np.ascontiguousarray(big_skips, dtype=np.uintp)
+        fi = np.ascontiguousarray(fun_index, dtype=np.uintp).ravel()
+        self._check(self.L.b200jk_set_layout(self.h, nbf, naux, ss.ctypes.data_as(_szp), bs.ctypes.data_as(_szp),
+                                             fi.ctypes.data_as(_szp)))
+        self.nbf, self.naux = int(nbf), int(naux)
+        self._small_skips, self._big_skips = ss, bs
+
+    def upload(self, which, packed):
+        p = np.ascontiguousarray(packed, dtype=np.float64)
+        if p.size != int(self._big_skips[self.nbf]):
+            raise B200JKError(1, f"packed tensor has {p.size} doubles, layout says {int(self._big_skips[self.nbf])}")
+        self._check(self.L.b200jk_upload(self.h, which, _d(p)))
+
+    def upload_rows(self, which, m0, m1, rows):
+        p = np.ascontiguousarray(rows, dtype=np.float64)
+        need = int(self._big_skips[m1] - self._big_skips[m0])
+        if p.size != need:
+            raise B200JKError(1, f"row block has {p.size} doubles, layout says {need}")
+        self._check(self.L.b200jk_upload_rows(self.h, which, m0, m1, _d(p)))
+
+    def fill_synthetic(self, which, seed, amp):
+        a = np.ascontiguousarray(amp, dtype=np.float64)
+        assert a.shape == (self.nbf, self.nbf)
+        self._check(self.L.b200jk_fill_synthetic(self.h, which, ct.c_uint64(seed), _d(a)))
+
+    def download_rows(self, which, m, q0, q1):
+        sp = int(self._small_skips[m])
+        out = np.zeros((q1 - q0, sp))
+        self._check(self.L.b200jk_download_rows(self.h, which, m, q0, q1, _d(out)))
+        return out
+
+    def compute(self, Cl, Cr, D, do_J=True, do_K=True, do_wK=False):
+        """Host-operand build.  Cl/Cr: lists of (nbf, nocc_i) arrays (Cr None => lr_symmetric);
+        D: list of (nbf,nbf).  Returns (J, K, wK) lists (None where untasked)."""
+        n = self.nbf
+        nmat = len(Cl) if Cl is not None else len(D)
+        Cl_ = None if Cl is None else [np.ascontiguousarray(c, dtype=np.float64).reshape(n, -1) for c in Cl]
+        Cr_ = None if Cr is None else [np.ascontiguousarray(c, dtype=np.float64).reshape(n, -1) for c in Cr]
+        D_ = None if D is None else [np.ascontiguousarray(d, dtype=np.float64) for d in D]
+        nocc = (ct.c_int * nmat)(*([c.shape[1] for c in Cl_] if Cl_ is not None else [0] * nmat))
+        J = [np.empty((n, n)) for _ in range(nmat)] if do_J else None
+        K = [np.empty((n, n)) for _ in range(nmat)] if do_K else None
+        wK = [np.empty((n, n)) for _ in range(nmat)] if do_wK else None
+        rc = self.L.b200jk_compute(self.h, nmat, _ptr_array(Cl_), _ptr_array(Cr_), nocc, _ptr_array(D_),
+                                   _ptr_array(J), _ptr_array(K), _ptr_array(wK), int(do_J), int(do_K), int(do_wK))
+        self._check(rc)
+        return J, K, wK
+
+    # -- device-resident operands (kernel-only timing) --
+    def dev_alloc(self, nbytes) -> int:
+        p = ct.c_void_p()
+        self._check(self.L.b200jk_dev_alloc(self.h, nbytes, ct.byref(p)))
+        return p.value
+
+    def dev_free(self, p):
+        self._check(self.L.b200jk_dev_free(self.h, ct.c_void_p(p)))
+
+    def dev_put(self, arr) -> int:
+        a = np.ascontiguousarray(arr, dtype=np.float64)
+        p = self.dev_alloc(a.nbytes)
+        self._check(self.L.b200jk_dev_copy(self.h, ct.c_void_p(p), a.ctypes.data_as(ct.c_void_p), a.nbytes, 1))
+        return p
+
+    def dev_get(self, p, shape):
+        out = np.empty(shape)
+        self._check(self.L.b200jk_dev_copy(self.h, out.ctypes.data_as(ct.c_void_p), ct.c_void_p(p), out.nbytes, 2))
+        return out
+
+    def compute_device(self, dCl, dCr, nocc, dD, dJ, dK, dwK, do_J=True, do_K=True, do_wK=False):
+        nmat = len(nocc)
+
+        def arr(ps):
+            if ps is None:
+                return None
+            return ct.cast((ct.c_void_p * nmat)(*ps), _dpp)
+
+        no = (ct.c_int * nmat)(*nocc)
+        self._check(self.L.b200jk_compute_device(self.h, nmat, arr(dCl), arr(dCr), no, arr(dD), arr(dJ), arr(dK),
+                                                 arr(dwK), int(do_J), int(do_K), int(do_wK)))
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self.L.b200jk_get_stats(self.h, ct.byref(s)))
+        return s.as_dict()
+
+    def hbm_estimate(self, max_nocc, do_wK=False) -> int:
+        v = ct.c_uint64()
+        self._check(self.L.b200jk_hbm_estimate(self.h, max_nocc, int(do_wK), ct.byref(v)))
+        return v.value
+
+    def set_work_budget(self, nbytes):
+        self._check(self.L.b200jk_set_work_budget(self.h, nbytes))
+
+    def fp64_peak(self, kind) -> float:
+        v = ct.c_double()
+        self._check(self.L.b200jk_fp64_peak(self.h, kind, ct.byref(v)))
+        return v.value
