@@ -173,9 +173,11 @@ class Engine:
         D: list of (nbf,nbf).  Returns (J, K, wK) lists (None where untasked)."""
         n = self.nbf
         nmat = len(Cl) if Cl is not None else len(D)
+        if not n:
+            raise B200JKError(1, "b200jk_compute before b200jk_set_layout")
         Cl_ = None if Cl is None else [np.ascontiguousarray(c, dtype=np.float64).reshape(n, -1) for c in Cl]
         Cr_ = None if Cr is None else [np.ascontiguousarray(c, dtype=np.float64).reshape(n, -1) for c in Cr]
-        D_ = None if D is None else [np.ascontiguousarray(d, dtype=np.float64) for d in D]
+        D_ = None if D is None else [np.ascontiguousarray(d, dtype=np.float64).reshape(n, n) for d in D]
         nocc = (ct.c_int * nmat)(*([c.shape[1] for c in Cl_] if Cl_ is not None else [0] * nmat))
         J = [np.empty((n, n)) for _ in range(nmat)] if do_J else None
         K = [np.empty((n, n)) for _ in range(nmat)] if do_K else None
