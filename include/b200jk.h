@@ -161,9 +161,12 @@ int b200jk_dev_alloc(b200jk_t* h, size_t bytes, void** dptr);
 int b200jk_dev_free(b200jk_t* h, void* dptr);
 int b200jk_dev_copy(b200jk_t* h, void* dst, const void* src, size_t bytes, int kind /*1=H2D 2=D2H 3=D2D*/);
 
-/* FP64 calibration kernels (register-resident DMMA / DFMA loops) -> TFLOP/s, for the roofline
- * denominator that MEASURED_PEAKS.json lacks. kind: 0 = DMMA m8n8k4, 1 = DFMA. */
-int b200jk_fp64_peak(b200jk_t* h, int kind, double* tflops);
+/* FP64 calibration kernels (register-resident loops, no memory traffic) for the roofline denominator that
+ * MEASURED_PEAKS.json lacks.  kind: 0 = DMMA m8n8k4, 1 = DFMA, 2 = both interleaved in every warp.
+ * out4 = { burst TFLOP/s (best single launch from idle), sustained TFLOP/s (back-to-back launches for
+ * `seconds`), SM MHz during the burst launch, SM MHz during the last sustained launch }; the clocks come
+ * from clock64()/globaltimer inside the kernel. */
+int b200jk_fp64_peak(b200jk_t* h, int kind, double seconds, double* out4);
 
 #ifdef __cplusplus
 }

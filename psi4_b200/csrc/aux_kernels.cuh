@@ -68,36 +68,42 @@ __global__ void synth_fill_kernel(double* __restrict__ tensor, const size_t* __r
 }
 
 // ---- FP64 ceilings: register-resident loops, no memory traffic ---------------------------------
-__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
+// kind 0: DMMA m8n8k4 only; 1: DFMA only; 2: both interleaved in every warp (are they one pipe?).
+// Each block also reports (clock64 delta, globaltimer delta) so the SM clock under this load is
+// measured from inside the kernel rather than sampled by nvidia-smi.
+template <int KIND>
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, unsigned long long* clk, int iters) {
     double c[16][2];
+    double f[16];
 #pragma unroll
-    for (int i = 0; i < 16; i++) c[i][0] = c[i][1] = 0.0;
+    for (int i = 0; i < 16; i++) {
+        c[i][0] = c[i][1] = 0.0;
+        f[i] = threadIdx.x * 1e-3 + i;
+    }
     double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    unsigned long long t0, t1, g0, g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+    t0 = clock64();
     for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int i = 0; i < 16; i++)
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                         : "+d"(c[i][0]), "+d"(c[i][1])
-                         : "d"(a), "d"(b));
+        for (int i = 0; i < 16; i++) {
+            if (KIND == 0 || KIND == 2)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(c[i][0]), "+d"(c[i][1])
+                             : "d"(a), "d"(b));
+            if (KIND == 1 || KIND == 2) f[i] = fma(f[i], a, b);
+        }
     }
+    t1 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
     double s = 0;
 #pragma unroll
-    for (int i = 0; i < 16; i++) s += c[i][0] + c[i][1];
+    for (int i = 0; i < 16; i++) s += c[i][0] + c[i][1] + f[i];
     if (s == 123.456) out[0] = s;
-}
-__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) {
-    double c[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) c[i] = threadIdx.x * 1e-3 + i;
-    double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9;
-    for (int it = 0; it < iters; it++) {
-#pragma unroll
-        for (int i = 0; i < 16; i++) c[i] = fma(c[i], a, b);
+    if (threadIdx.x == 0) {
+        clk[2 * blockIdx.x] = t1 - t0;
+        clk[2 * blockIdx.x + 1] = g1 - g0;
     }
-    double s = 0;
-#pragma unroll
-    for (int i = 0; i < 16; i++) s += c[i];
-    if (s == 123.456) out[0] = s;
 }
 
 }  // namespace b2k

@@ -75,24 +75,34 @@ __device__ __forceinline__ void load_tile_gather(double* s, const double* __rest
     }
 }
 
-// One BK=16 stage of DMMAs for this warp.  mbv / nbv = number of live 8-row / 8-col blocks
-// (warp-uniform), so dead edge blocks cost nothing.
-template <int NB>
+// One BK=16 stage of DMMAs for this warp.  FULL: every 8x8 block of the warp tile is live -> no
+// predicates at all (a predicated mma.sync costs WARPSYNC + branch per DMMA and serialises the pipe).
+// Otherwise mbv / nbv = number of live 8-row / 8-col blocks (warp-uniform): dead edge blocks are skipped.
+template <int NB, bool FULL>
 __device__ __forceinline__ void mma_stage(const double* __restrict__ As, const double* __restrict__ Bs,
                                           double (&acc)[4][NB][2], int wm, int wn, int g, int t, int mbv, int nbv) {
+    const double* Ap = As + (wm * 32 + g) * LDT + t;
+    const double* Bp = Bs + (wn * 8 * NB + g) * LDT + t;
 #pragma unroll
     for (int ks = 0; ks < BK / 4; ks++) {
         double a[4], b[NB];
 #pragma unroll
-        for (int mb = 0; mb < 4; mb++) a[mb] = As[(wm * 32 + mb * 8 + g) * LDT + ks * 4 + t];
+        for (int mb = 0; mb < 4; mb++) a[mb] = Ap[mb * 8 * LDT + ks * 4];
 #pragma unroll
-        for (int nb = 0; nb < NB; nb++) b[nb] = Bs[(wn * 8 * NB + nb * 8 + g) * LDT + ks * 4 + t];
+        for (int nb = 0; nb < NB; nb++) b[nb] = Bp[nb * 8 * LDT + ks * 4];
+        if (FULL) {
 #pragma unroll
-        for (int mb = 0; mb < 4; mb++) {
-            if (mb < mbv) {
+            for (int mb = 0; mb < 4; mb++)
 #pragma unroll
-                for (int nb = 0; nb < NB; nb++)
-                    if (nb < nbv) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+                for (int nb = 0; nb < NB; nb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+        } else {
+#pragma unroll
+            for (int mb = 0; mb < 4; mb++) {
+                if (mb < mbv) {
+#pragma unroll
+                    for (int nb = 0; nb < NB; nb++)
+                        if (nb < nbv) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+                }
             }
         }
     }
@@ -152,6 +162,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) half_transform_kernel(HalfPar
 
     const int mbv = max(0, min(4, (p.qc - (q0 + wm * 32) + 7) / 8));
     const int nbv = max(0, min(NB, (icols - wn * 8 * NB + 7) / 8));
+    const bool full = (mbv == 4) && (nbv == NB);
 
     double acc[4][NB][2];
 #pragma unroll
@@ -190,7 +201,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) half_transform_kernel(HalfPar
         if (!dense) col_next = fetch_col(kt + STAGES);
         issue(kt + STAGES - 1, col);
         int st = kt % STAGES;
-        mma_stage<NB>(As + st * BM * LDT, Bs + st * BN * LDT, acc, wm, wn, g, t, mbv, nbv);
+        if (full)
+            mma_stage<NB, true>(As + st * BM * LDT, Bs + st * BN * LDT, acc, wm, wn, g, t, mbv, nbv);
+        else
+            mma_stage<NB, false>(As + st * BM * LDT, Bs + st * BN * LDT, acc, wm, wn, g, t, mbv, nbv);
     }
     cp_async_wait<0>();
 
@@ -262,6 +276,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) kgemm_kernel(KgemmParams p) {
     double* Bs = smem + STAGES * BM * LDT;
     const int mbv = max(0, min(4, (p.nbf - (m0 + wm * 32) + 7) / 8));
     const int nbv = max(0, min(NB, (p.nbf - (n0 + wn * 8 * NB) + 7) / 8));
+    const bool full = (mbv == 4) && (nbv == NB);
 
     double acc[4][NB][2];
 #pragma unroll
@@ -284,7 +299,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) kgemm_kernel(KgemmParams p) {
         __syncthreads();
         issue(kt + STAGES - 1);
         int st = kt % STAGES;
-        mma_stage<NB>(As + st * BM * LDT, Bs + st * BN * LDT, acc, wm, wn, g, t, mbv, nbv);
+        if (full)
+            mma_stage<NB, true>(As + st * BM * LDT, Bs + st * BN * LDT, acc, wm, wn, g, t, mbv, nbv);
+        else
+            mma_stage<NB, false>(As + st * BM * LDT, Bs + st * BN * LDT, acc, wm, wn, g, t, mbv, nbv);
     }
     cp_async_wait<0>();
 

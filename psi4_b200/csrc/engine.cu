@@ -1050,37 +1050,74 @@ int b200jk_dev_copy(b200jk_t* h, void* dst, const void* src, size_t bytes, int k
     return 0;
 }
 
-int b200jk_fp64_peak(b200jk_t* h, int kind, double* tflops) {
-    if (!h || !tflops || h->sh.empty()) return B200JK_ERR_INVALID;
+int b200jk_fp64_peak(b200jk_t* h, int kind, double seconds, double* out4) {
+    if (!h || !out4 || h->sh.empty() || kind < 0 || kind > 2) return B200JK_ERR_INVALID;
     Shard& s = h->sh[0];
     CK(cudaSetDevice(s.dev));
     int nsm = 148;
     CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s.dev));
+    const int iters = 4000, blocks = nsm * 4, threads = 256;
     double* out = nullptr;
+    unsigned long long* clk = nullptr;
     CK(cudaMalloc((void**)&out, 8));
+    CK(cudaMalloc((void**)&clk, sizeof(unsigned long long) * 2 * blocks));
+    std::vector<unsigned long long> hclk(2 * blocks);
     cudaEvent_t a, b;
     CK(cudaEventCreate(&a));
     CK(cudaEventCreate(&b));
-    const int iters = 20000, blocks = nsm * 4, threads = 256;
-    double best = 0;
-    for (int rep = 0; rep < 4; rep++) {
-        CK(cudaEventRecord(a, s.stream));
+    const double flops = (double)blocks * threads * iters * 16.0 *
+                         ((kind == 0 || kind == 2 ? 512.0 / 32.0 : 0.0) + (kind == 1 || kind == 2 ? 2.0 : 0.0));
+    auto launch = [&]() {
         if (kind == 0)
-            dmma_peak_kernel<<<blocks, threads, 0, s.stream>>>(out, iters);
+            fp64_peak_kernel<0><<<blocks, threads, 0, s.stream>>>(out, clk, iters);
+        else if (kind == 1)
+            fp64_peak_kernel<1><<<blocks, threads, 0, s.stream>>>(out, clk, iters);
         else
-            dfma_peak_kernel<<<blocks, threads, 0, s.stream>>>(out, iters);
+            fp64_peak_kernel<2><<<blocks, threads, 0, s.stream>>>(out, clk, iters);
+    };
+    auto mhz = [&]() {
+        cudaMemcpy(hclk.data(), clk, sizeof(unsigned long long) * 2 * blocks, cudaMemcpyDeviceToHost);
+        double cyc = 0, ns = 0;
+        for (int i = 0; i < blocks; i++) {
+            cyc += (double)hclk[2 * i];
+            ns += (double)hclk[2 * i + 1];
+        }
+        return ns > 0 ? cyc / ns * 1e3 : 0.0;
+    };
+    // burst: best single launch out of a few, from idle
+    CK(cudaStreamSynchronize(s.stream));
+    double burst = 0, burst_mhz = 0;
+    for (int rep = 0; rep < 3; rep++) {
+        CK(cudaEventRecord(a, s.stream));
+        launch();
         CK(cudaEventRecord(b, s.stream));
         CK(cudaEventSynchronize(b));
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, a, b));
-        double flops = kind == 0 ? (double)blocks * (threads / 32) * iters * 16.0 * 512.0
-                                 : (double)blocks * threads * iters * 16.0 * 2.0;
-        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > burst) {
+            burst = tf;
+            burst_mhz = mhz();
+        }
     }
+    // sustained: back-to-back launches for `seconds`
+    int n = 0;
+    float total_ms = 0;
+    CK(cudaEventRecord(a, s.stream));
+    do {
+        for (int k = 0; k < 8; k++, n++) launch();
+        CK(cudaEventRecord(b, s.stream));
+        CK(cudaEventSynchronize(b));
+        CK(cudaEventElapsedTime(&total_ms, a, b));
+    } while (total_ms < seconds * 1e3);
+    out4[0] = burst;
+    out4[1] = flops * n / (total_ms * 1e-3) / 1e12;
+    out4[2] = burst_mhz;
+    out4[3] = mhz();
     CK(cudaEventDestroy(a));
     CK(cudaEventDestroy(b));
     CK(cudaFree(out));
-    *tflops = best;
+    CK(cudaFree(clk));
     return 0;
 }
 

@@ -65,7 +65,7 @@ SIGNATURES = {
     "b200jk_dev_alloc": (ct.c_int, [ct.c_void_p, ct.c_size_t, ct.POINTER(ct.c_void_p)]),
     "b200jk_dev_free": (ct.c_int, [ct.c_void_p, ct.c_void_p]),
     "b200jk_dev_copy": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_size_t, ct.c_int]),
-    "b200jk_fp64_peak": (ct.c_int, [ct.c_void_p, ct.c_int, _dp]),
+    "b200jk_fp64_peak": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_double, _dp]),
 }
 
 
@@ -232,7 +232,7 @@ class Engine:
     def set_work_budget(self, nbytes):
         self._check(self.L.b200jk_set_work_budget(self.h, nbytes))
 
-    def fp64_peak(self, kind) -> float:
-        v = ct.c_double()
-        self._check(self.L.b200jk_fp64_peak(self.h, kind, ct.byref(v)))
-        return v.value
+    def fp64_peak(self, kind, seconds=1.0) -> dict:
+        v = (ct.c_double * 4)()
+        self._check(self.L.b200jk_fp64_peak(self.h, kind, float(seconds), v))
+        return {"burst_tflops": v[0], "sustained_tflops": v[1], "burst_sm_mhz": v[2], "sustained_sm_mhz": v[3]}

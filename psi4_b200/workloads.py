@@ -12,6 +12,8 @@ CONFIGS = {
     "c20h42_tz": dict(nbf=1188, naux=2840, nocc=81, nmat=1, band=0.55),
     "c60_tz": dict(nbf=1800, naux=4740, nocc=180, nmat=1, band=None),
     "h2o40_tz": dict(nbf=2320, naux=5560, nocc=200, nmat=2, band=0.6),
+    # one eighth of C60's auxiliary index (what each GPU holds at 8 GPUs): short enough for ncu --set full
+    "c60_tz_q8": dict(nbf=1800, naux=592, nocc=180, nmat=1, band=None),
 }
 SEED = 20251017
 

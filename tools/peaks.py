@@ -8,5 +8,5 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from psi4_b200 import Engine  # noqa: E402
 
 e = Engine(1)
-out = {"dmma_tflops": e.fp64_peak(0), "dfma_tflops": e.fp64_peak(1)}
+out = {"dmma": e.fp64_peak(0, 2.0), "dfma": e.fp64_peak(1, 2.0), "dmma+dfma": e.fp64_peak(2, 2.0)}
 print(json.dumps(out))
