@@ -1,0 +1,100 @@
+"""Multi-GPU parity (-m gpu, skipped below 2 devices): both ways of driving N GPUs -- one process
+(psi4's situation: b200jk_create(ngpu)) and one process per GPU (torchrun: b200jk_create_rank)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    import torch
+
+    return torch.cuda.device_count()
+
+
+def _case(rng, oracle):
+    from psi4_b200 import DFHelper
+
+    n, a = 90, 131
+    r = rng.random((n, n))
+    keep = (r + r.T) < 1.4
+    np.fill_diagonal(keep, True)
+    d = DFHelper(n, a)
+    d.prepare_sparsity(keep=keep)
+    B = rng.standard_normal((a, n, n)) * 0.1
+    B = B + B.transpose(0, 2, 1)
+    P = d.pack(B)
+    Cl = [rng.standard_normal((n, 13)), rng.standard_normal((n, 4))]
+    Cr = [rng.standard_normal((n, 13)), rng.standard_normal((n, 4))]
+    return d, oracle.Sparsity(keep, a), P, Cl, Cr
+
+
+@pytest.mark.parametrize("lr", [True, False])
+def test_single_process_multi_gpu(oracle, lr):
+    if _ngpu() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from psi4_b200 import Engine
+
+    rng = np.random.default_rng(8)
+    d, sp, P, Cl, Cr = _case(rng, oracle)
+    Cr = None if lr else Cr
+    D = [x @ (x if lr else y).T for x, y in zip(Cl, Cl if lr else Cr)]
+    Jo, Ko, _, _ = oracle.build_JK(sp, P, Cl, Cr, D=D)
+    for ng in [g for g in (2, 4, 8) if g <= _ngpu()]:
+        e = Engine(ng)
+        e.set_layout(d.nbf_, d.naux_, d.small_skips_, d.big_skips_, d.schwarz_fun_index_)
+        e.upload(0, P)
+        J, K, _ = e.compute(Cl, Cr, D)
+        for i in range(2):
+            assert np.abs(J[i] - Jo[i]).max() < 1e-10
+            assert np.abs(K[i] - Ko[i]).max() < 1e-10
+        assert e.stats()["n_shards"] == ng
+        e.close()
+
+
+RANK_SCRIPT = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["B2_ROOT"]); sys.path.insert(0, os.path.join(os.environ["B2_ROOT"], "oracle"))
+sys.path.insert(0, os.path.join(os.environ["B2_ROOT"], "tests"))
+import dfjk_oracle as oracle
+from psi4_b200 import Engine
+from test_gpu_multi import _case
+rank, world, lrk = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lrk)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lrk))
+idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+if rank == 0:
+    idt = torch.tensor(list(Engine.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+dist.broadcast(idt, 0)
+d, sp, P, Cl, Cr = _case(np.random.default_rng(8), oracle)
+e = Engine(rank=rank, world=world, device=lrk, nccl_id=bytes(idt.cpu().tolist()))
+e.set_layout(d.nbf_, d.naux_, d.small_skips_, d.big_skips_, d.schwarz_fun_index_)
+e.upload(0, P)   # every rank holds the host tensor here; the engine copies only its Q shard
+J, K, _ = e.compute(Cl, Cr, [x @ y.T for x, y in zip(Cl, Cr)])
+Jo, Ko, _, _ = oracle.build_JK(sp, P, Cl, Cr)
+err = max(max(np.abs(J[i] - Jo[i]).max(), np.abs(K[i] - Ko[i]).max()) for i in range(2))
+st = e.stats()
+print(f"RANK{rank} err={err:.3e} q=[{st['q_begin']},{st['q_end']}) allreduce_ms={st['ms_allreduce']:.3f}", flush=True)
+assert err < 1e-10
+dist.barrier(); dist.destroy_process_group()
+"""
+
+
+def test_one_process_per_gpu_torchrun(tmp_path):
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    script = tmp_path / "rank.py"
+    script.write_text(RANK_SCRIPT)
+    env = dict(os.environ, B2_ROOT=ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 2)}",
+           "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "RANK0 err=" in r.stdout and "RANK1 err=" in r.stdout
