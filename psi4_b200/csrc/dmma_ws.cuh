@@ -1,0 +1,391 @@
+// dmma_ws.cuh -- persistent, warp-specialised FP64 tensor-core pipeline for the two compute-bound
+// kernels of the DF-K build (second generation of dmma_gemm.cuh, same math, same tile shapes):
+//
+//   K3  half_ws_kernel<NB>  : T[m,q,i] = sum_k B_m[q,k] * C[n_k,i]      (lib3index/dfhelper.cc:2162-2186)
+//   K4  kgemm_ws_kernel     : K[m,n]  += sum_{q,i} T1[m,qi] * T2[n,qi]  (lib3index/dfhelper.cc:3374)
+//
+// One CTA per SM, 12 warps = 3 warpgroups (registers re-balanced with setmaxnreg: 40 / 232 / 232):
+//   warps 0..3  producer warpgroup.  One elected lane issues TMA tile loads (cp.async.bulk.tensor.2d,
+//               SWIZZLE_128B, completion on an mbarrier); when a row-block is screened (sp(m) < nbf) all
+//               128 producer threads gather the C operand along the kept-partner list with 8-byte cp.async
+//               into the same swizzled layout and signal the same mbarrier (cp.async.mbarrier.arrive.noinc).
+//   warps 4..11 consumers.  4 (M) x 2 (N) warp grid, warp tile 32 x 8*NB, DMMA m8n8k4 with register
+//               accumulators.  They wait on full[stage], read fragments, and release empty[stage].
+// No __syncthreads in the main loop: warps drift apart, so while one warp waits for data or stores its
+// tile the other warp on the same scheduler keeps the DMMA pipe busy.  The CTA is persistent over a
+// static round-robin list of work items, so the producer prefetches the next item's first stages while
+// the consumers are still in the epilogue of the previous one.
+//
+// Shared tile = rows x 128 bytes (16 doubles of k), TMA 128-byte swizzle: 16-byte chunk c of row r lands
+// at chunk c ^ (r & 7).  DMMA k-step s of a stage uses k = {2s, 2s+1, 2s+8, 2s+9} (a permutation of k is
+// free in a dot product as long as both operands agree): lane (g = lane/4, t = lane%4) reads chunk
+// (s + 4*(t/2)) ^ g, half t%2 -- the 16 lanes of a half-warp then hit 16 distinct 8-byte bank pairs.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dmma_gemm.cuh"
+
+namespace b2k {
+
+constexpr int WS_STAGES = 6;
+constexpr int WS_CONSUMER_WARPS = 8;
+constexpr int WS_PRODUCER_WARPS = 4;   // one warpgroup (setmaxnreg works per warpgroup)
+constexpr int WS_PRODUCER_THREADS = 32 * WS_PRODUCER_WARPS;
+constexpr int WS_THREADS = 32 * (WS_CONSUMER_WARPS + WS_PRODUCER_WARPS);
+constexpr int WS_ROW_BYTES = 128;            // BK doubles
+constexpr int WS_A_STAGE = BM * WS_ROW_BYTES;  // 16 KB
+
+template <int NB>
+constexpr size_t ws_smem_bytes() {
+    return 1024 + (size_t)WS_STAGES * (WS_A_STAGE + 16 * NB * WS_ROW_BYTES) + 2 * WS_STAGES * sizeof(uint64_t);
+}
+
+// ---- mbarrier / TMA primitives (PTX ISA 8.x, sm_90+) -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(n)
+                 : "memory");
+}
+__device__ __forceinline__ void reg_dealloc_producer() { asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n"); }
+__device__ __forceinline__ void reg_alloc_consumer() { asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar), ok;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(map) : "memory");
+}
+
+// One stage (16 k) of DMMAs from swizzled tiles.  a_row / b_row point at this lane's first fragment
+// row (row & 7 == g); off[s] is the lane's swizzled byte offset for k-step s.
+template <int NB, bool FULL>
+__device__ __forceinline__ void mma_stage_swz(const uint8_t* __restrict__ a_row, const uint8_t* __restrict__ b_row,
+                                              const int (&off)[4], double (&acc)[4][NB][2], int mbv, int nbv) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+        double a[4], b[NB];
+#pragma unroll
+        for (int mb = 0; mb < 4; mb++) a[mb] = *reinterpret_cast<const double*>(a_row + mb * 8 * WS_ROW_BYTES + off[ks]);
+#pragma unroll
+        for (int nb = 0; nb < NB; nb++) b[nb] = *reinterpret_cast<const double*>(b_row + nb * 8 * WS_ROW_BYTES + off[ks]);
+        if (FULL) {
+#pragma unroll
+            for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+                for (int nb = 0; nb < NB; nb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+        } else {
+#pragma unroll
+            for (int mb = 0; mb < 4; mb++) {
+                if (mb < mbv) {
+#pragma unroll
+                    for (int nb = 0; nb < NB; nb++)
+                        if (nb < nbv) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+                }
+            }
+        }
+    }
+}
+
+struct WsCarve {
+    uint8_t* As;
+    uint8_t* Bs;
+    uint64_t* full;
+    uint64_t* empty;
+};
+template <int NB>
+__device__ __forceinline__ WsCarve ws_carve(uint8_t* raw) {
+    WsCarve c;
+    // offset arithmetic (not an integer round trip) so the compiler keeps the shared address space -> LDS, not LD
+    uint8_t* base = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
+    c.As = base;
+    c.Bs = base + WS_STAGES * WS_A_STAGE;
+    c.full = reinterpret_cast<uint64_t*>(c.Bs + WS_STAGES * 16 * NB * WS_ROW_BYTES);
+    c.empty = c.full + WS_STAGES;
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3, persistent.  Work item w -> (it, qt, m): it fastest so the CTAs sharing an A tile run together.
+// ---------------------------------------------------------------------------------------------
+struct HalfWsParams {
+    const CUtensorMap* amaps;   // [nbf] per-row-block maps of the shard tensor: dims {sp(m), nq}, pitch ld(m)
+    const int* sp;              // [nbf]
+    const int* cols;            // kept-partner lists
+    const size_t* cols_off;     // [nbf]
+    const double* Ct;           // [o x ldc] (gather source)
+    int ldc;
+    int o, op, iw;
+    int nit, nqt;               // i tiles, q tiles per row-block
+    int qbeg, qc;               // chunk of the shard's Q rows
+    int nbf;
+    int nitems;
+    double* T;                  // [nbf][qc][op]
+};
+
+template <int NB>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+    half_ws_kernel(const __grid_constant__ CUtensorMap ctmap, HalfWsParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int BN = 16 * NB;
+    constexpr int B_STAGE = BN * WS_ROW_BYTES;
+    WsCarve sm = ws_carve<NB>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        for (int s = 0; s < WS_STAGES; s++) {
+            mbar_init(&sm.full[s], 1 + WS_PRODUCER_THREADS);  // expect_tx arrive + one arrive per producer thread
+            mbar_init(&sm.empty[s], WS_CONSUMER_WARPS);  // one arrive per consumer warp
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp < WS_PRODUCER_WARPS) {
+        // ================= producer warpgroup =================
+        reg_dealloc_producer();
+        if (tid == 0) prefetch_tmap(&ctmap);
+        uint32_t g = 0;  // global stage counter
+        const int kk = tid & 15;
+        const int chunk = kk >> 1, half = kk & 1;
+        for (int w = blockIdx.x; w < p.nitems; w += gridDim.x) {
+            const int it = w % p.nit;
+            const int qt = (w / p.nit) % p.nqt;
+            const int m = w / (p.nit * p.nqt);
+            const int K = p.sp[m];
+            const int nkt = (K + BK - 1) / BK;
+            const bool dense = (K == p.nbf);
+            const int i0 = it * p.iw;
+            if (dense) {
+                // both operands by TMA; one thread drives the whole stage
+                if (tid == 0) {
+                    const CUtensorMap* amap = p.amaps + m;
+                    for (int kt = 0; kt < nkt; kt++) {
+                        const uint32_t gg = g + kt;
+                        const int s = gg % WS_STAGES;
+                        mbar_wait(&sm.empty[s], ((gg / WS_STAGES) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&sm.full[s], WS_A_STAGE + B_STAGE);
+                        tma_load_2d(sm.As + s * WS_A_STAGE, amap, kt * BK, p.qbeg + qt * BM, &sm.full[s]);
+                        tma_load_2d(sm.Bs + s * B_STAGE, &ctmap, kt * BK, i0, &sm.full[s]);
+                        mbar_arrive_n(&sm.full[s], WS_PRODUCER_THREADS);
+                    }
+                }
+                g += nkt;
+                continue;
+            }
+            const int irows = min(p.o, i0 + BN) - i0;  // valid C^T rows of this tile
+            const CUtensorMap* amap = p.amaps + m;
+            const int* cols = p.cols + p.cols_off[m];
+            int col_next = (kk < K) ? __ldg(cols + kk) : -1;
+            for (int kt = 0; kt < nkt; kt++, g++) {
+                const int s = g % WS_STAGES;
+                const uint32_t ph = (g / WS_STAGES) & 1;
+                mbar_wait(&sm.empty[s], ph ^ 1);
+                if (tid == 0) {
+                    mbar_arrive_expect_tx(&sm.full[s], WS_A_STAGE);
+                    tma_load_2d(sm.As + s * WS_A_STAGE, amap, kt * BK, p.qbeg + qt * BM, &sm.full[s]);
+                }
+                const int col = col_next;
+                const int kn = (kt + 1) * BK + kk;
+                col_next = (kt + 1 < nkt && kn < K) ? __ldg(cols + kn) : -1;
+                uint8_t* bs = sm.Bs + s * B_STAGE;
+#pragma unroll 4
+                for (int r = tid >> 4; r < BN; r += WS_PRODUCER_THREADS / 16) {
+                    int bytes = (col >= 0 && r < irows) ? 8 : 0;
+                    const double* src = bytes ? p.Ct + (size_t)(i0 + r) * p.ldc + col : p.Ct;
+                    double* dst = reinterpret_cast<double*>(bs + r * WS_ROW_BYTES + ((chunk ^ (r & 7)) << 4) + (half << 3));
+                    cp_async8(dst, src, bytes);
+                }
+                cp_async_mbar_arrive_noinc(&sm.full[s]);
+            }
+        }
+        cp_async_wait<0>();
+        return;
+    }
+
+    // ================= consumers =================
+    reg_alloc_consumer();
+    const int cw = warp - WS_PRODUCER_WARPS;
+    const int wm = cw & 3, wn = cw >> 2, gq = lane >> 2, t = lane & 3;
+    int off[4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) off[ks] = (((ks + 4 * (t >> 1)) ^ gq) << 4) + ((t & 1) << 3);
+    const int a_row0 = (wm * 32 + gq) * WS_ROW_BYTES;
+    const int b_row0 = (wn * 8 * NB + gq) * WS_ROW_BYTES;
+    uint32_t g = 0;
+    for (int w = blockIdx.x; w < p.nitems; w += gridDim.x) {
+        const int it = w % p.nit;
+        const int qt = (w / p.nit) % p.nqt;
+        const int m = w / (p.nit * p.nqt);
+        const int K = p.sp[m];
+        const int nkt = (K + BK - 1) / BK;
+        const int q0 = qt * BM, i0 = it * p.iw;
+        const int icols = min(p.iw, p.o - i0);
+        const int mbv = max(0, min(4, (p.qc - (q0 + wm * 32) + 7) / 8));
+        const int nbv = max(0, min(NB, (icols - wn * 8 * NB + 7) / 8));
+        const bool full = (mbv == 4) && (nbv == NB);
+        double acc[4][NB][2];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < NB; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+        for (int kt = 0; kt < nkt; kt++, g++) {
+            const int s = g % WS_STAGES;
+            const uint32_t ph = (g / WS_STAGES) & 1;
+            mbar_wait(&sm.full[s], ph);
+            const uint8_t* a_row = sm.As + s * WS_A_STAGE + a_row0;
+            const uint8_t* b_row = sm.Bs + s * B_STAGE + b_row0;
+            if (full)
+                mma_stage_swz<NB, true>(a_row, b_row, off, acc, mbv, nbv);
+            else
+                mma_stage_swz<NB, false>(a_row, b_row, off, acc, mbv, nbv);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[s]);
+        }
+
+        double* Tm = p.T + (size_t)m * p.qc * p.op;
+#pragma unroll
+        for (int mb = 0; mb < 4; mb++) {
+            int q = q0 + wm * 32 + mb * 8 + gq;
+            if (q < p.qc) {
+#pragma unroll
+                for (int nb = 0; nb < NB; nb++) {
+                    int ic = wn * 8 * NB + nb * 8 + t * 2;
+                    int i = i0 + ic;
+                    if (ic < p.iw && i < p.op)
+                        *reinterpret_cast<double2*>(Tm + (size_t)q * p.op + i) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4, persistent.  Work item w -> (tile, split): the tiles of one split run together (L2 reuse of T).
+// ---------------------------------------------------------------------------------------------
+struct KgemmWsParams {
+    int nbf, kdim, klen, ntile1d, symmetric, ntiles, nitems;
+    double* ws;  // [nsplit][ntiles][128*128]
+};
+
+__global__ void __launch_bounds__(WS_THREADS, 1)
+    kgemm_ws_kernel(const __grid_constant__ CUtensorMap t1map, const __grid_constant__ CUtensorMap t2map, KgemmWsParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int NB = 8, BN = 128;
+    constexpr int B_STAGE = BN * WS_ROW_BYTES;
+    WsCarve sm = ws_carve<NB>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < WS_STAGES; s++) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], WS_CONSUMER_WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp < WS_PRODUCER_WARPS) {
+        reg_dealloc_producer();
+        if (tid == 0) {
+            prefetch_tmap(&t1map);
+            prefetch_tmap(&t2map);
+            uint32_t g = 0;
+            for (int w = blockIdx.x; w < p.nitems; w += gridDim.x) {
+                int tm, tn;
+                tile_coords(w % p.ntiles, p.ntile1d, p.symmetric, tm, tn);
+                const int kb = (w / p.ntiles) * p.klen;
+                const int ke = min(p.kdim, kb + p.klen);
+                const int nkt = (ke - kb + BK - 1) / BK;
+                for (int kt = 0; kt < nkt; kt++, g++) {
+                    const int s = g % WS_STAGES;
+                    const uint32_t ph = (g / WS_STAGES) & 1;
+                    mbar_wait(&sm.empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&sm.full[s], WS_A_STAGE + B_STAGE);
+                    tma_load_2d(sm.As + s * WS_A_STAGE, &t1map, kb + kt * BK, tm * BM, &sm.full[s]);
+                    tma_load_2d(sm.Bs + s * B_STAGE, &t2map, kb + kt * BK, tn * BN, &sm.full[s]);
+                }
+            }
+        }
+        return;
+    }
+
+    reg_alloc_consumer();
+    const int cw = warp - WS_PRODUCER_WARPS;
+    const int wm = cw & 3, wn = cw >> 2, gq = lane >> 2, t = lane & 3;
+    int off[4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) off[ks] = (((ks + 4 * (t >> 1)) ^ gq) << 4) + ((t & 1) << 3);
+    const int a_row0 = (wm * 32 + gq) * WS_ROW_BYTES;
+    const int b_row0 = (wn * 8 * NB + gq) * WS_ROW_BYTES;
+    uint32_t g = 0;
+    for (int w = blockIdx.x; w < p.nitems; w += gridDim.x) {
+        int tm, tn;
+        tile_coords(w % p.ntiles, p.ntile1d, p.symmetric, tm, tn);
+        const int kb = (w / p.ntiles) * p.klen;
+        const int ke = min(p.kdim, kb + p.klen);
+        const int nkt = (ke - kb + BK - 1) / BK;
+        const int mbv = max(0, min(4, (p.nbf - (tm * BM + wm * 32) + 7) / 8));
+        const int nbv = max(0, min(NB, (p.nbf - (tn * BN + wn * 8 * NB) + 7) / 8));
+        const bool full = (mbv == 4) && (nbv == NB);
+        double acc[4][NB][2];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < NB; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+        for (int kt = 0; kt < nkt; kt++, g++) {
+            const int s = g % WS_STAGES;
+            const uint32_t ph = (g / WS_STAGES) & 1;
+            mbar_wait(&sm.full[s], ph);
+            const uint8_t* a_row = sm.As + s * WS_A_STAGE + a_row0;
+            const uint8_t* b_row = sm.Bs + s * B_STAGE + b_row0;
+            if (full)
+                mma_stage_swz<NB, true>(a_row, b_row, off, acc, mbv, nbv);
+            else
+                mma_stage_swz<NB, false>(a_row, b_row, off, acc, mbv, nbv);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[s]);
+        }
+        double* wsp = p.ws + (size_t)w * (BM * BN);
+#pragma unroll
+        for (int mb = 0; mb < 4; mb++) {
+            int r = wm * 32 + mb * 8 + gq;
+#pragma unroll
+            for (int nb = 0; nb < NB; nb++) {
+                int c = wn * 8 * NB + nb * 8 + t * 2;
+                *reinterpret_cast<double2*>(wsp + r * BN + c) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+            }
+        }
+    }
+}
+
+}  // namespace b2k

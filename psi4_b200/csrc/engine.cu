@@ -5,8 +5,10 @@
 // (Q|mn) tensor resident in HBM, sharded over the auxiliary index Q.
 //
 // No CPU fallback: every entry point that needs a device fails with an error code if none.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -18,6 +20,7 @@
 #include "../../include/b200jk.h"
 #include "aux_kernels.cuh"
 #include "dmma_gemm.cuh"
+#include "dmma_ws.cuh"
 #include "j_kernels.cuh"
 
 using namespace b2k;
@@ -74,6 +77,8 @@ struct Shard {
     int q0 = 0, q1 = 0, nq = 0;
     cudaStream_t stream = nullptr;
     double* tensor[3] = {nullptr, nullptr, nullptr};
+    CUtensorMap* d_amaps[3] = {nullptr, nullptr, nullptr};  // per-row-block TMA descriptors of each tensor
+    int nsm = 148;
     size_t tensor_doubles = 0;
     size_t* d_row_off = nullptr;
     int *d_ldm = nullptr, *d_sp = nullptr, *d_ign = nullptr, *d_cols = nullptr;
@@ -208,6 +213,136 @@ void choose_split(int ntiles, int kdim, int nsm, int* nsplit, int* klen) {
     *nsplit = (kdim + kl - 1) / kl;
 }
 
+
+// ---- TMA descriptors ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+int load_encode(b200jk* h) {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || !fn || q != cudaDriverEntryPointSuccess)
+        return fail(h, B200JK_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    g_encode = (EncodeTiledFn)fn;
+    return 0;
+}
+
+// 2-D f64 tensor map: `inner` contiguous elements per row, `rows` rows of pitch_bytes; box = 16 x box_rows,
+// 128-byte swizzle, out-of-bounds elements read as zero (ragged k tails / edge rows need no masking).
+int make_map(b200jk* h, CUtensorMap* out, const double* base, uint64_t inner, uint64_t rows, uint64_t pitch_bytes,
+             uint32_t box_rows) {
+    cuuint64_t dims[2] = {inner, rows};
+    cuuint64_t strides[1] = {pitch_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(h, B200JK_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%llu rows=%llu pitch=%llu", (int)r,
+                    (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)pitch_bytes);
+    return 0;
+}
+
+bool use_legacy() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200JK_LEGACY");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
+template <int NB>
+int launch_half_ws(b200jk* h, Shard& s, const CUtensorMap& ctmap, const HalfWsParams& p) {
+    static bool attr_set[64] = {false};
+    constexpr size_t smem = ws_smem_bytes<NB>();
+    if (!attr_set[s.dev]) {
+        CK(cudaFuncSetAttribute(half_ws_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[s.dev] = true;
+    }
+    int grid = std::min(p.nitems, s.nsm);
+    half_ws_kernel<NB><<<grid, WS_THREADS, smem, s.stream>>>(ctmap, p);
+    s.launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int run_half_ws(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o, int op, int qbeg, int qc, double* T) {
+    int nit = (o + 127) / 128;
+    int iw = round_up((op + nit - 1) / nit, 2);
+    int NB = (iw + 15) / 16;
+    CUtensorMap ctmap;
+    int rc = make_map(h, &ctmap, Ct, h->nbf, (uint64_t)o, (uint64_t)ldc * 8, (uint32_t)(16 * NB));
+    if (rc) return rc;
+    HalfWsParams p;
+    p.amaps = s.d_amaps[which];
+    p.sp = s.d_sp;
+    p.cols = s.d_cols;
+    p.cols_off = s.d_cols_off;
+    p.Ct = Ct;
+    p.ldc = ldc;
+    p.o = o;
+    p.op = op;
+    p.iw = iw;
+    p.nit = nit;
+    p.nqt = (qc + BM - 1) / BM;
+    p.qbeg = qbeg;
+    p.qc = qc;
+    p.nbf = (int)h->nbf;
+    p.nitems = nit * p.nqt * (int)h->nbf;
+    p.T = T;
+    switch (NB) {
+        case 1: return launch_half_ws<1>(h, s, ctmap, p);
+        case 2: return launch_half_ws<2>(h, s, ctmap, p);
+        case 3: return launch_half_ws<3>(h, s, ctmap, p);
+        case 4: return launch_half_ws<4>(h, s, ctmap, p);
+        case 5: return launch_half_ws<5>(h, s, ctmap, p);
+        case 6: return launch_half_ws<6>(h, s, ctmap, p);
+        case 7: return launch_half_ws<7>(h, s, ctmap, p);
+        default: return launch_half_ws<8>(h, s, ctmap, p);
+    }
+}
+
+int run_kgemm_ws(b200jk* h, Shard& s, const double* T1, const double* T2, int kdim, bool symmetric, double* Kout) {
+    static bool attr_set[64] = {false};
+    constexpr size_t smem = ws_smem_bytes<8>();
+    if (!attr_set[s.dev]) {
+        CK(cudaFuncSetAttribute(kgemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[s.dev] = true;
+    }
+    int n1d = ((int)h->nbf + BM - 1) / BM;
+    int ntiles = symmetric ? n1d * (n1d + 1) / 2 : n1d * n1d;
+    int nsplit, klen;
+    choose_split(ntiles, kdim, s.nsm, &nsplit, &klen);
+    size_t need = (size_t)nsplit * ntiles * BM * 128;
+    int rc = grow(h, &s.ws, &s.ws_cap, need);
+    if (rc) return rc;
+    CUtensorMap m1, m2;
+    if ((rc = make_map(h, &m1, T1, (uint64_t)kdim, h->nbf, (uint64_t)kdim * 8, BM))) return rc;
+    if ((rc = make_map(h, &m2, T2, (uint64_t)kdim, h->nbf, (uint64_t)kdim * 8, 128))) return rc;
+    KgemmWsParams p;
+    p.nbf = (int)h->nbf;
+    p.kdim = kdim;
+    p.klen = klen;
+    p.ntile1d = n1d;
+    p.symmetric = symmetric ? 1 : 0;
+    p.ntiles = ntiles;
+    p.nitems = ntiles * nsplit;
+    p.ws = s.ws;
+    kgemm_ws_kernel<<<std::min(p.nitems, s.nsm), WS_THREADS, smem, s.stream>>>(m1, m2, p);
+    s.launches++;
+    CK(cudaGetLastError());
+    kgemm_reduce_kernel<<<ntiles, 256, 0, s.stream>>>(s.ws, nsplit, ntiles, n1d, p.symmetric, p.nbf, Kout);
+    s.launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 template <int NB>
 int launch_half(b200jk* h, Shard& s, const HalfParams& p, dim3 grid) {
     static bool attr_set[64] = {false};
@@ -223,8 +358,9 @@ int launch_half(b200jk* h, Shard& s, const HalfParams& p, dim3 grid) {
 }
 
 // T[m][q][i] for q in the chunk [qbeg, qbeg+qc): one launch over (i-tiles, q-tiles, m).
-int run_half(b200jk* h, Shard& s, const double* tensor, const double* Ct, int ldc, int o, int op, int qbeg, int qc,
-             double* T) {
+int run_half(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o, int op, int qbeg, int qc, double* T) {
+    if (!use_legacy()) return run_half_ws(h, s, which, Ct, ldc, o, op, qbeg, qc, T);
+    const double* tensor = s.tensor[which];
     int nit = (o + 127) / 128;
     int iw = round_up((op + nit - 1) / nit, 2);
     int NB = (iw + 15) / 16;
@@ -258,6 +394,7 @@ int run_half(b200jk* h, Shard& s, const double* tensor, const double* Ct, int ld
 }
 
 int run_kgemm(b200jk* h, Shard& s, const double* T1, const double* T2, int kdim, bool symmetric, double* Kout) {
+    if (!use_legacy()) return run_kgemm_ws(h, s, T1, T2, kdim, symmetric, Kout);
     static bool attr_set[64] = {false};
     constexpr size_t smem = gemm_smem_bytes<8>();
     if (!attr_set[s.dev]) {
@@ -429,8 +566,8 @@ int run_device(b200jk* h, Shard& s, const Task& t, const double* const* dCl, con
     for (int pass = 0; pass < 2; pass++) {
         bool wk = pass == 1;
         if (wk ? !t.do_wK : !t.do_K) continue;
-        const double* tenL = s.tensor[wk ? B200JK_TENSOR_M1PPQ : B200JK_TENSOR_PPQ];
-        const double* tenR = s.tensor[wk ? B200JK_TENSOR_WPPQ : B200JK_TENSOR_PPQ];
+        const int tenL = wk ? B200JK_TENSOR_M1PPQ : B200JK_TENSOR_PPQ;
+        const int tenR = wk ? B200JK_TENSOR_WPPQ : B200JK_TENSOR_PPQ;
         for (int i = 0; i < t.nmat; i++) {
             int o = t.nocc[i];
             if (!o) continue;  // dfhelper.cc:3354-3357
@@ -560,15 +697,18 @@ int setup_shards(b200jk* h, int n, const int* devs) {
         if (s.dev < 0 || s.dev >= ndev) return fail(h, B200JK_ERR_INVALID, "device %d out of range (%d visible)", s.dev, ndev);
         CK(cudaSetDevice(s.dev));
         CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CK(cudaDeviceGetAttribute(&s.nsm, cudaDevAttrMultiProcessorCount, s.dev));
     }
-    return 0;
+    return load_encode(h);
 }
 
 void free_shard(Shard& s) {
     cudaSetDevice(s.dev);
     if (s.stream) cudaStreamSynchronize(s.stream);
-    for (int w = 0; w < 3; w++)
+    for (int w = 0; w < 3; w++) {
         if (s.tensor[w]) cudaFree(s.tensor[w]);
+        if (s.d_amaps[w]) cudaFree(s.d_amaps[w]);
+    }
     void* ptrs[] = {s.d_row_off, s.d_ldm, s.d_sp, s.d_ign, s.d_cols, s.d_cols_off, s.in, s.out,
                     s.Ctl,       s.Ctr,   s.dpart, s.T1,  s.T2,     s.ws};
     for (void* p : ptrs)
@@ -592,6 +732,17 @@ int alloc_tensor(b200jk* h, int which) {
                         need / 1073741824.0, s.dev, free_b / 1073741824.0);
         CK(cudaMalloc((void**)&s.tensor[which], std::max<size_t>(need, 8)));
         CK(cudaMemsetAsync(s.tensor[which], 0, need, s.stream));
+        // one TMA descriptor per row-block m: dims {sp(m), nq}, row pitch ld(m) doubles
+        std::vector<CUtensorMap> maps(h->nbf);
+        if (s.nq > 0) {
+            for (size_t m = 0; m < h->nbf; m++) {
+                int rc = make_map(h, &maps[m], s.tensor[which] + h->row_off_unit[m] * (size_t)s.nq, (uint64_t)h->sp[m],
+                                  (uint64_t)s.nq, (uint64_t)h->ldm[m] * 8, BM);
+                if (rc) return rc;
+            }
+        }
+        CK(cudaMalloc((void**)&s.d_amaps[which], sizeof(CUtensorMap) * h->nbf));
+        CK(cudaMemcpy(s.d_amaps[which], maps.data(), sizeof(CUtensorMap) * h->nbf, cudaMemcpyHostToDevice));
     }
     return 0;
 }
