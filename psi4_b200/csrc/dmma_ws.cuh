@@ -12,9 +12,11 @@
 //   warps 4..11 consumers.  4 (M) x 2 (N) warp grid, warp tile 32 x 8*NB, DMMA m8n8k4 with register
 //               accumulators.  They wait on full[stage], read fragments, and release empty[stage].
 // No __syncthreads in the main loop: warps drift apart, so while one warp waits for data or stores its
-// tile the other warp on the same scheduler keeps the DMMA pipe busy.  The CTA is persistent over a
-// static round-robin list of work items, so the producer prefetches the next item's first stages while
-// the consumers are still in the epilogue of the previous one.
+// tile the other warp on the same scheduler keeps the DMMA pipe busy.  The CTA is persistent: the producer
+// pulls work items from a global atomic counter (dynamic scheduling: edge tiles and screened row-blocks
+// cost less than interior ones, a static split leaves SMs idle) and tags the first stage of each item with
+// its id, so the consumers need no other communication; the producer prefetches the next item's first
+// stages while the consumers are still in the epilogue of the previous one.
 //
 // Shared tile = rows x 128 bytes (16 doubles of k), TMA 128-byte swizzle: 16-byte chunk c of row r lands
 // at chunk c ^ (r & 7).  DMMA k-step s of a stage uses k = {2s, 2s+1, 2s+8, 2s+9} (a permutation of k is
@@ -39,7 +41,8 @@ constexpr int WS_A_STAGE = BM * WS_ROW_BYTES;  // 16 KB
 
 template <int NB>
 constexpr size_t ws_smem_bytes() {
-    return 1024 + (size_t)WS_STAGES * (WS_A_STAGE + 16 * NB * WS_ROW_BYTES) + 2 * WS_STAGES * sizeof(uint64_t);
+    return 1024 + (size_t)WS_STAGES * (WS_A_STAGE + 16 * NB * WS_ROW_BYTES) + 2 * WS_STAGES * sizeof(uint64_t) +
+           (WS_STAGES + 2) * sizeof(int);
 }
 
 // ---- mbarrier / TMA primitives (PTX ISA 8.x, sm_90+) -------------------------------------------------
@@ -57,6 +60,7 @@ __device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
 }
 __device__ __forceinline__ void reg_dealloc_producer() { asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n"); }
 __device__ __forceinline__ void reg_alloc_consumer() { asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n"); }
+__device__ __forceinline__ void producer_bar_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(WS_PRODUCER_THREADS) : "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(smem_u32(bar)),
                  "r"(bytes)
@@ -116,11 +120,56 @@ __device__ __forceinline__ void mma_stage_swz(const uint8_t* __restrict__ a_row,
     }
 }
 
+// Same stage with all four row blocks live and exactly LIVE (compile-time) column blocks: an unpredicated
+// DMMA stream for ragged nocc tiles (the predicated generic path costs a WARPSYNC + branch per DMMA).
+template <int NB, int LIVE>
+__device__ __forceinline__ void mma_stage_live(const uint8_t* __restrict__ a_row, const uint8_t* __restrict__ b_row,
+                                               const int (&off)[4], double (&acc)[4][NB][2]) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+        double a[4], b[LIVE];
+#pragma unroll
+        for (int mb = 0; mb < 4; mb++) a[mb] = *reinterpret_cast<const double*>(a_row + mb * 8 * WS_ROW_BYTES + off[ks]);
+#pragma unroll
+        for (int nb = 0; nb < LIVE; nb++) b[nb] = *reinterpret_cast<const double*>(b_row + nb * 8 * WS_ROW_BYTES + off[ks]);
+#pragma unroll
+        for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+            for (int nb = 0; nb < LIVE; nb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+    }
+}
+template <int NB, int LIVE>
+struct StageDispatch {
+    static __device__ __forceinline__ void run(const uint8_t* a_row, const uint8_t* b_row, const int (&off)[4],
+                                               double (&acc)[4][NB][2], int nbv) {
+        if (nbv == LIVE)
+            mma_stage_live<NB, LIVE>(a_row, b_row, off, acc);
+        else
+            StageDispatch<NB, LIVE - 1>::run(a_row, b_row, off, acc, nbv);
+    }
+};
+template <int NB>
+struct StageDispatch<NB, 0> {
+    static __device__ __forceinline__ void run(const uint8_t*, const uint8_t*, const int (&)[4], double (&)[4][NB][2], int) {}
+};
+// mbv / nbv are warp-uniform: all-rows-live tiles take a specialised unpredicated stream, the last q tile of a
+// shard (mbv < 4, one item in ~38) takes the predicated generic path.
+template <int NB>
+__device__ __forceinline__ void mma_stage_any(const uint8_t* a_row, const uint8_t* b_row, const int (&off)[4],
+                                              double (&acc)[4][NB][2], int mbv, int nbv) {
+    if (mbv == 4)
+        StageDispatch<NB, NB>::run(a_row, b_row, off, acc, nbv);
+    else
+        mma_stage_swz<NB, false>(a_row, b_row, off, acc, mbv, nbv);
+}
+
 struct WsCarve {
     uint8_t* As;
     uint8_t* Bs;
     uint64_t* full;
     uint64_t* empty;
+    volatile int* meta;   // [WS_STAGES] item id carried by the first stage of an item (-1 = no more work)
+    volatile int* sched;  // [2] producer-group broadcast slots for the next item id
 };
 template <int NB>
 __device__ __forceinline__ WsCarve ws_carve(uint8_t* raw) {
@@ -131,6 +180,8 @@ __device__ __forceinline__ WsCarve ws_carve(uint8_t* raw) {
     c.Bs = base + WS_STAGES * WS_A_STAGE;
     c.full = reinterpret_cast<uint64_t*>(c.Bs + WS_STAGES * 16 * NB * WS_ROW_BYTES);
     c.empty = c.full + WS_STAGES;
+    c.meta = reinterpret_cast<volatile int*>(c.empty + WS_STAGES);
+    c.sched = c.meta + WS_STAGES;
     return c;
 }
 
@@ -149,6 +200,7 @@ struct HalfWsParams {
     int qbeg, qc;               // chunk of the shard's Q rows
     int nbf;
     int nitems;
+    int* counter;               // work queue head (zeroed before launch)
     double* T;                  // [nbf][qc][op]
 };
 
@@ -164,9 +216,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
     if (tid == 0) {
         for (int s = 0; s < WS_STAGES; s++) {
             mbar_init(&sm.full[s], 1 + WS_PRODUCER_THREADS);  // expect_tx arrive + one arrive per producer thread
-            mbar_init(&sm.empty[s], WS_CONSUMER_WARPS);  // one arrive per consumer warp
+            mbar_init(&sm.empty[s], WS_CONSUMER_WARPS);       // one arrive per consumer warp
         }
         mbar_fence_init();
+        sm.sched[0] = atomicAdd(p.counter, 1);
     }
     __syncthreads();
 
@@ -177,7 +230,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         uint32_t g = 0;  // global stage counter
         const int kk = tid & 15;
         const int chunk = kk >> 1, half = kk & 1;
-        for (int w = blockIdx.x; w < p.nitems; w += gridDim.x) {
+        int slot = 0;
+        int w = sm.sched[0];
+        while (w < p.nitems) {
+            int w_next = 0;
+            if (tid == 0) w_next = atomicAdd(p.counter, 1);  // latency hidden behind this item's k loop
             const int it = w % p.nit;
             const int qt = (w / p.nit) % p.nqt;
             const int m = w / (p.nit * p.nqt);
@@ -185,14 +242,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
             const int nkt = (K + BK - 1) / BK;
             const bool dense = (K == p.nbf);
             const int i0 = it * p.iw;
+            const CUtensorMap* amap = p.amaps + m;
             if (dense) {
                 // both operands by TMA; one thread drives the whole stage
                 if (tid == 0) {
-                    const CUtensorMap* amap = p.amaps + m;
                     for (int kt = 0; kt < nkt; kt++) {
                         const uint32_t gg = g + kt;
                         const int s = gg % WS_STAGES;
                         mbar_wait(&sm.empty[s], ((gg / WS_STAGES) & 1) ^ 1);
+                        if (kt == 0) sm.meta[s] = w;
                         mbar_arrive_expect_tx(&sm.full[s], WS_A_STAGE + B_STAGE);
                         tma_load_2d(sm.As + s * WS_A_STAGE, amap, kt * BK, p.qbeg + qt * BM, &sm.full[s]);
                         tma_load_2d(sm.Bs + s * B_STAGE, &ctmap, kt * BK, i0, &sm.full[s]);
@@ -200,33 +258,44 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
                     }
                 }
                 g += nkt;
-                continue;
-            }
-            const int irows = min(p.o, i0 + BN) - i0;  // valid C^T rows of this tile
-            const CUtensorMap* amap = p.amaps + m;
-            const int* cols = p.cols + p.cols_off[m];
-            int col_next = (kk < K) ? __ldg(cols + kk) : -1;
-            for (int kt = 0; kt < nkt; kt++, g++) {
-                const int s = g % WS_STAGES;
-                const uint32_t ph = (g / WS_STAGES) & 1;
-                mbar_wait(&sm.empty[s], ph ^ 1);
-                if (tid == 0) {
-                    mbar_arrive_expect_tx(&sm.full[s], WS_A_STAGE);
-                    tma_load_2d(sm.As + s * WS_A_STAGE, amap, kt * BK, p.qbeg + qt * BM, &sm.full[s]);
-                }
-                const int col = col_next;
-                const int kn = (kt + 1) * BK + kk;
-                col_next = (kt + 1 < nkt && kn < K) ? __ldg(cols + kn) : -1;
-                uint8_t* bs = sm.Bs + s * B_STAGE;
+            } else {
+                const int irows = min(p.o, i0 + BN) - i0;  // valid C^T rows of this tile
+                const int* cols = p.cols + p.cols_off[m];
+                int col_next = (kk < K) ? __ldg(cols + kk) : -1;
+                for (int kt = 0; kt < nkt; kt++, g++) {
+                    const int s = g % WS_STAGES;
+                    const uint32_t ph = (g / WS_STAGES) & 1;
+                    mbar_wait(&sm.empty[s], ph ^ 1);
+                    if (tid == 0) {
+                        if (kt == 0) sm.meta[s] = w;
+                        mbar_arrive_expect_tx(&sm.full[s], WS_A_STAGE);
+                        tma_load_2d(sm.As + s * WS_A_STAGE, amap, kt * BK, p.qbeg + qt * BM, &sm.full[s]);
+                    }
+                    const int col = col_next;
+                    const int kn = (kt + 1) * BK + kk;
+                    col_next = (kt + 1 < nkt && kn < K) ? __ldg(cols + kn) : -1;
+                    uint8_t* bs = sm.Bs + s * B_STAGE;
 #pragma unroll 4
-                for (int r = tid >> 4; r < BN; r += WS_PRODUCER_THREADS / 16) {
-                    int bytes = (col >= 0 && r < irows) ? 8 : 0;
-                    const double* src = bytes ? p.Ct + (size_t)(i0 + r) * p.ldc + col : p.Ct;
-                    double* dst = reinterpret_cast<double*>(bs + r * WS_ROW_BYTES + ((chunk ^ (r & 7)) << 4) + (half << 3));
-                    cp_async8(dst, src, bytes);
+                    for (int r = tid >> 4; r < BN; r += WS_PRODUCER_THREADS / 16) {
+                        int bytes = (col >= 0 && r < irows) ? 8 : 0;
+                        const double* src = bytes ? p.Ct + (size_t)(i0 + r) * p.ldc + col : p.Ct;
+                        double* dst =
+                            reinterpret_cast<double*>(bs + r * WS_ROW_BYTES + ((chunk ^ (r & 7)) << 4) + (half << 3));
+                        cp_async8(dst, src, bytes);
+                    }
+                    cp_async_mbar_arrive_noinc(&sm.full[s]);
                 }
-                cp_async_mbar_arrive_noinc(&sm.full[s]);
             }
+            if (tid == 0) sm.sched[slot ^ 1] = w_next;
+            producer_bar_sync();
+            slot ^= 1;
+            w = sm.sched[slot];
+        }
+        if (tid == 0) {  // sentinel stage: tells every consumer warp to stop
+            const int s = g % WS_STAGES;
+            mbar_wait(&sm.empty[s], ((g / WS_STAGES) & 1) ^ 1);
+            sm.meta[s] = -1;
+            mbar_arrive_n(&sm.full[s], 1 + WS_PRODUCER_THREADS);
         }
         cp_async_wait<0>();
         return;
@@ -242,7 +311,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
     const int a_row0 = (wm * 32 + gq) * WS_ROW_BYTES;
     const int b_row0 = (wn * 8 * NB + gq) * WS_ROW_BYTES;
     uint32_t g = 0;
-    for (int w = blockIdx.x; w < p.nitems; w += gridDim.x) {
+    for (;;) {
+        int s = g % WS_STAGES;
+        mbar_wait(&sm.full[s], (g / WS_STAGES) & 1);
+        const int w = sm.meta[s];
+        if (w < 0) break;
         const int it = w % p.nit;
         const int qt = (w / p.nit) % p.nqt;
         const int m = w / (p.nit * p.nqt);
@@ -252,7 +325,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         const int icols = min(p.iw, p.o - i0);
         const int mbv = max(0, min(4, (p.qc - (q0 + wm * 32) + 7) / 8));
         const int nbv = max(0, min(NB, (icols - wn * 8 * NB + 7) / 8));
-        const bool full = (mbv == 4) && (nbv == NB);
         double acc[4][NB][2];
 #pragma unroll
         for (int a = 0; a < 4; a++)
@@ -260,15 +332,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
             for (int b = 0; b < NB; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
 
         for (int kt = 0; kt < nkt; kt++, g++) {
-            const int s = g % WS_STAGES;
-            const uint32_t ph = (g / WS_STAGES) & 1;
-            mbar_wait(&sm.full[s], ph);
+            if (kt > 0) {
+                s = g % WS_STAGES;
+                mbar_wait(&sm.full[s], (g / WS_STAGES) & 1);
+            }
             const uint8_t* a_row = sm.As + s * WS_A_STAGE + a_row0;
             const uint8_t* b_row = sm.Bs + s * B_STAGE + b_row0;
-            if (full)
-                mma_stage_swz<NB, true>(a_row, b_row, off, acc, mbv, nbv);
-            else
-                mma_stage_swz<NB, false>(a_row, b_row, off, acc, mbv, nbv);
+            mma_stage_any<NB>(a_row, b_row, off, acc, mbv, nbv);
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.empty[s]);
         }
@@ -291,11 +361,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
 }
 
 // ---------------------------------------------------------------------------------------------
-// K4, persistent.  Work item w -> (tile, split): the tiles of one split run together (L2 reuse of T).
+// K4, persistent.  Work item w -> (tile = w % ntiles, split = w / ntiles): the tiles of one split run
+// together (L2 reuse of T); `tiles` lists (tm, tn) by decreasing live area so the cheap edge tiles of the
+// last split fill the tail.
 // ---------------------------------------------------------------------------------------------
 struct KgemmWsParams {
-    int nbf, kdim, klen, ntile1d, symmetric, ntiles, nitems;
-    double* ws;  // [nsplit][ntiles][128*128]
+    int nbf, kdim, klen, ntiles, nitems;
+    const int2* tiles;  // [ntiles] (tm, tn)
+    int* counter;
+    double* ws;         // [nsplit][ntiles][128*128]
 };
 
 __global__ void __launch_bounds__(WS_THREADS, 1)
@@ -320,21 +394,27 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
             prefetch_tmap(&t1map);
             prefetch_tmap(&t2map);
             uint32_t g = 0;
-            for (int w = blockIdx.x; w < p.nitems; w += gridDim.x) {
-                int tm, tn;
-                tile_coords(w % p.ntiles, p.ntile1d, p.symmetric, tm, tn);
+            int w = atomicAdd(p.counter, 1);
+            while (w < p.nitems) {
+                const int w_next = atomicAdd(p.counter, 1);
+                const int2 tl = p.tiles[w % p.ntiles];
                 const int kb = (w / p.ntiles) * p.klen;
                 const int ke = min(p.kdim, kb + p.klen);
                 const int nkt = (ke - kb + BK - 1) / BK;
                 for (int kt = 0; kt < nkt; kt++, g++) {
                     const int s = g % WS_STAGES;
-                    const uint32_t ph = (g / WS_STAGES) & 1;
-                    mbar_wait(&sm.empty[s], ph ^ 1);
+                    mbar_wait(&sm.empty[s], ((g / WS_STAGES) & 1) ^ 1);
+                    if (kt == 0) sm.meta[s] = w;
                     mbar_arrive_expect_tx(&sm.full[s], WS_A_STAGE + B_STAGE);
-                    tma_load_2d(sm.As + s * WS_A_STAGE, &t1map, kb + kt * BK, tm * BM, &sm.full[s]);
-                    tma_load_2d(sm.Bs + s * B_STAGE, &t2map, kb + kt * BK, tn * BN, &sm.full[s]);
+                    tma_load_2d(sm.As + s * WS_A_STAGE, &t1map, kb + kt * BK, tl.x * BM, &sm.full[s]);
+                    tma_load_2d(sm.Bs + s * B_STAGE, &t2map, kb + kt * BK, tl.y * BN, &sm.full[s]);
                 }
+                w = w_next;
             }
+            const int s = g % WS_STAGES;
+            mbar_wait(&sm.empty[s], ((g / WS_STAGES) & 1) ^ 1);
+            sm.meta[s] = -1;
+            mbar_arrive(&sm.full[s]);
         }
         return;
     }
@@ -348,30 +428,30 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
     const int a_row0 = (wm * 32 + gq) * WS_ROW_BYTES;
     const int b_row0 = (wn * 8 * NB + gq) * WS_ROW_BYTES;
     uint32_t g = 0;
-    for (int w = blockIdx.x; w < p.nitems; w += gridDim.x) {
-        int tm, tn;
-        tile_coords(w % p.ntiles, p.ntile1d, p.symmetric, tm, tn);
+    for (;;) {
+        int s = g % WS_STAGES;
+        mbar_wait(&sm.full[s], (g / WS_STAGES) & 1);
+        const int w = sm.meta[s];
+        if (w < 0) break;
+        const int2 tl = p.tiles[w % p.ntiles];
         const int kb = (w / p.ntiles) * p.klen;
         const int ke = min(p.kdim, kb + p.klen);
         const int nkt = (ke - kb + BK - 1) / BK;
-        const int mbv = max(0, min(4, (p.nbf - (tm * BM + wm * 32) + 7) / 8));
-        const int nbv = max(0, min(NB, (p.nbf - (tn * BN + wn * 8 * NB) + 7) / 8));
-        const bool full = (mbv == 4) && (nbv == NB);
+        const int mbv = max(0, min(4, (p.nbf - (tl.x * BM + wm * 32) + 7) / 8));
+        const int nbv = max(0, min(NB, (p.nbf - (tl.y * BN + wn * 8 * NB) + 7) / 8));
         double acc[4][NB][2];
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
             for (int b = 0; b < NB; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
         for (int kt = 0; kt < nkt; kt++, g++) {
-            const int s = g % WS_STAGES;
-            const uint32_t ph = (g / WS_STAGES) & 1;
-            mbar_wait(&sm.full[s], ph);
+            if (kt > 0) {
+                s = g % WS_STAGES;
+                mbar_wait(&sm.full[s], (g / WS_STAGES) & 1);
+            }
             const uint8_t* a_row = sm.As + s * WS_A_STAGE + a_row0;
             const uint8_t* b_row = sm.Bs + s * B_STAGE + b_row0;
-            if (full)
-                mma_stage_swz<NB, true>(a_row, b_row, off, acc, mbv, nbv);
-            else
-                mma_stage_swz<NB, false>(a_row, b_row, off, acc, mbv, nbv);
+            mma_stage_any<NB>(a_row, b_row, off, acc, mbv, nbv);
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.empty[s]);
         }
@@ -384,6 +464,23 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
                 int c = wn * 8 * NB + nb * 8 + t * 2;
                 *reinterpret_cast<double2*>(wsp + r * BN + c) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
             }
+        }
+    }
+}
+
+// K[m][n] += sum_s ws[s][tile][r][c]  (fixed order); mirrored for off-diagonal tiles when symmetric.
+__global__ void kgemm_reduce_list_kernel(const double* __restrict__ ws, int nsplit, int ntiles,
+                                         const int2* __restrict__ tiles, int symmetric, int nbf, double* __restrict__ K) {
+    const int tile = blockIdx.x;
+    const int2 tl = tiles[tile];
+    for (int e = threadIdx.x; e < BM * 128; e += blockDim.x) {
+        int r = e >> 7, c = e & 127;
+        int m = tl.x * BM + r, n = tl.y * 128 + c;
+        if (m < nbf && n < nbf) {
+            double s = 0.0;
+            for (int sp = 0; sp < nsplit; sp++) s += ws[((size_t)sp * ntiles + tile) * (BM * 128) + e];
+            K[(size_t)m * nbf + n] += s;
+            if (symmetric && tl.y > tl.x) K[(size_t)n * nbf + m] += s;
         }
     }
 }

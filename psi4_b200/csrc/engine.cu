@@ -79,6 +79,9 @@ struct Shard {
     double* tensor[3] = {nullptr, nullptr, nullptr};
     CUtensorMap* d_amaps[3] = {nullptr, nullptr, nullptr};  // per-row-block TMA descriptors of each tensor
     int nsm = 148;
+    int* d_counter = nullptr;  // work-queue head of the persistent kernels
+    int2 *d_tiles_sym = nullptr, *d_tiles_full = nullptr;  // K-GEMM tile lists, largest live area first
+    int ntiles_sym = 0, ntiles_full = 0;
     size_t tensor_doubles = 0;
     size_t* d_row_off = nullptr;
     int *d_ldm = nullptr, *d_sp = nullptr, *d_ign = nullptr, *d_cols = nullptr;
@@ -266,6 +269,7 @@ int launch_half_ws(b200jk* h, Shard& s, const CUtensorMap& ctmap, const HalfWsPa
         attr_set[s.dev] = true;
     }
     int grid = std::min(p.nitems, s.nsm);
+    CK(cudaMemsetAsync(s.d_counter, 0, sizeof(int), s.stream));
     half_ws_kernel<NB><<<grid, WS_THREADS, smem, s.stream>>>(ctmap, p);
     s.launches++;
     CK(cudaGetLastError());
@@ -274,7 +278,8 @@ int launch_half_ws(b200jk* h, Shard& s, const CUtensorMap& ctmap, const HalfWsPa
 
 int run_half_ws(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o, int op, int qbeg, int qc, double* T) {
     int nit = (o + 127) / 128;
-    int iw = round_up((op + nit - 1) / nit, 2);
+    // orbital columns per tile: whole 8-column DMMA blocks, so a ragged nocc pads only the last block of the last tile
+    int iw = std::min(128, round_up((op + nit - 1) / nit, 8));
     int NB = (iw + 15) / 16;
     CUtensorMap ctmap;
     int rc = make_map(h, &ctmap, Ct, h->nbf, (uint64_t)o, (uint64_t)ldc * 8, (uint32_t)(16 * NB));
@@ -295,6 +300,7 @@ int run_half_ws(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o
     p.qc = qc;
     p.nbf = (int)h->nbf;
     p.nitems = nit * p.nqt * (int)h->nbf;
+    p.counter = s.d_counter;
     p.T = T;
     switch (NB) {
         case 1: return launch_half_ws<1>(h, s, ctmap, p);
@@ -315,10 +321,17 @@ int run_kgemm_ws(b200jk* h, Shard& s, const double* T1, const double* T2, int kd
         CK(cudaFuncSetAttribute(kgemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[s.dev] = true;
     }
-    int n1d = ((int)h->nbf + BM - 1) / BM;
-    int ntiles = symmetric ? n1d * (n1d + 1) / 2 : n1d * n1d;
-    int nsplit, klen;
-    choose_split(ntiles, kdim, s.nsm, &nsplit, &klen);
+    const int ntiles = symmetric ? s.ntiles_sym : s.ntiles_full;
+    const int2* tiles = symmetric ? s.d_tiles_sym : s.d_tiles_full;
+    // Dynamic scheduling: aim at ~16 work items per SM so the tail is one small item, while every item keeps
+    // >= 64 k-tiles (pipeline fill + partial-tile store amortised) and the partial-tile workspace stays <= 1 GiB.
+    const int nkt = (kdim + BK - 1) / BK;
+    int nsplit = (16 * s.nsm + ntiles - 1) / ntiles;
+    nsplit = std::min(nsplit, std::max(1, nkt / 64));
+    nsplit = (int)std::min<size_t>((size_t)nsplit, std::max<size_t>(1, ((size_t)1 << 30) / ((size_t)ntiles * BM * 128 * 8)));
+    nsplit = std::max(nsplit, 1);
+    const int klen = ((nkt + nsplit - 1) / nsplit) * BK;
+    nsplit = (kdim + klen - 1) / klen;
     size_t need = (size_t)nsplit * ntiles * BM * 128;
     int rc = grow(h, &s.ws, &s.ws_cap, need);
     if (rc) return rc;
@@ -329,15 +342,16 @@ int run_kgemm_ws(b200jk* h, Shard& s, const double* T1, const double* T2, int kd
     p.nbf = (int)h->nbf;
     p.kdim = kdim;
     p.klen = klen;
-    p.ntile1d = n1d;
-    p.symmetric = symmetric ? 1 : 0;
     p.ntiles = ntiles;
     p.nitems = ntiles * nsplit;
+    p.tiles = tiles;
+    p.counter = s.d_counter;
     p.ws = s.ws;
+    CK(cudaMemsetAsync(s.d_counter, 0, sizeof(int), s.stream));
     kgemm_ws_kernel<<<std::min(p.nitems, s.nsm), WS_THREADS, smem, s.stream>>>(m1, m2, p);
     s.launches++;
     CK(cudaGetLastError());
-    kgemm_reduce_kernel<<<ntiles, 256, 0, s.stream>>>(s.ws, nsplit, ntiles, n1d, p.symmetric, p.nbf, Kout);
+    kgemm_reduce_list_kernel<<<ntiles, 256, 0, s.stream>>>(s.ws, nsplit, ntiles, tiles, symmetric ? 1 : 0, p.nbf, Kout);
     s.launches++;
     CK(cudaGetLastError());
     return 0;
@@ -709,7 +723,8 @@ void free_shard(Shard& s) {
         if (s.tensor[w]) cudaFree(s.tensor[w]);
         if (s.d_amaps[w]) cudaFree(s.d_amaps[w]);
     }
-    void* ptrs[] = {s.d_row_off, s.d_ldm, s.d_sp, s.d_ign, s.d_cols, s.d_cols_off, s.in, s.out,
+    void* ptrs[] = {s.d_counter, s.d_tiles_sym, s.d_tiles_full,
+                    s.d_row_off, s.d_ldm, s.d_sp, s.d_ign, s.d_cols, s.d_cols_off, s.in, s.out,
                     s.Ctl,       s.Ctr,   s.dpart, s.T1,  s.T2,     s.ws};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -881,6 +896,23 @@ int b200jk_set_layout(b200jk_t* h, size_t nbf, size_t naux, const size_t* small_
         if ((rc = upload_vec(h, &s.d_ign, h->ign))) return rc;
         if ((rc = upload_vec(h, &s.d_cols, h->cols))) return rc;
         if ((rc = upload_vec(h, &s.d_cols_off, h->cols_off))) return rc;
+        {
+            // K-GEMM tile lists sorted by live area (rows x cols inside nbf), largest first
+            const int n1d = ((int)nbf + BM - 1) / BM;
+            auto live = [&](int t) { return std::min<int>(BM, (int)nbf - t * BM); };
+            for (int sym = 0; sym < 2; sym++) {
+                std::vector<int2> tl;
+                for (int a = 0; a < n1d; a++)
+                    for (int b = sym ? a : 0; b < n1d; b++) tl.push_back(make_int2(a, b));
+                std::stable_sort(tl.begin(), tl.end(), [&](const int2& x, const int2& y) {
+                    return live(x.x) * live(x.y) > live(y.x) * live(y.y);
+                });
+                if ((rc = upload_vec(h, sym ? &s.d_tiles_sym : &s.d_tiles_full, tl))) return rc;
+                (sym ? s.ntiles_sym : s.ntiles_full) = (int)tl.size();
+            }
+            std::vector<int> zero(1, 0);
+            if ((rc = upload_vec(h, &s.d_counter, zero))) return rc;
+        }
     }
     h->stats.q_begin = h->sh[0].q0;
     h->stats.q_end = h->sh[0].q1;
@@ -1202,12 +1234,13 @@ int b200jk_dev_copy(b200jk_t* h, void* dst, const void* src, size_t bytes, int k
 }
 
 int b200jk_fp64_peak(b200jk_t* h, int kind, double seconds, double* out4) {
-    if (!h || !out4 || h->sh.empty() || kind < 0 || kind > 2) return B200JK_ERR_INVALID;
+    if (!h || !out4 || h->sh.empty() || kind < 0 || kind > 4) return B200JK_ERR_INVALID;
     Shard& s = h->sh[0];
     CK(cudaSetDevice(s.dev));
     int nsm = 148;
     CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s.dev));
-    const int iters = 4000, blocks = nsm * 4, threads = 256;
+    // kinds 3 / 4: DMMA at the occupancy of the GEMM kernels (8 / 4 warps per SM, one CTA per SM)
+    const int iters = 4000, blocks = nsm * (kind >= 3 ? 1 : 4), threads = (kind == 4 ? 128 : 256);
     double* out = nullptr;
     unsigned long long* clk = nullptr;
     CK(cudaMalloc((void**)&out, 8));
@@ -1217,9 +1250,9 @@ int b200jk_fp64_peak(b200jk_t* h, int kind, double seconds, double* out4) {
     CK(cudaEventCreate(&a));
     CK(cudaEventCreate(&b));
     const double flops = (double)blocks * threads * iters * 16.0 *
-                         ((kind == 0 || kind == 2 ? 512.0 / 32.0 : 0.0) + (kind == 1 || kind == 2 ? 2.0 : 0.0));
+                         ((kind == 0 || kind >= 2 ? 512.0 / 32.0 : 0.0) + (kind == 1 || kind == 2 ? 2.0 : 0.0));
     auto launch = [&]() {
-        if (kind == 0)
+        if (kind == 0 || kind >= 3)
             fp64_peak_kernel<0><<<blocks, threads, 0, s.stream>>>(out, clk, iters);
         else if (kind == 1)
             fp64_peak_kernel<1><<<blocks, threads, 0, s.stream>>>(out, clk, iters);

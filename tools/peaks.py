@@ -8,5 +8,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from psi4_b200 import Engine  # noqa: E402
 
 e = Engine(1)
-out = {"dmma": e.fp64_peak(0, 2.0), "dfma": e.fp64_peak(1, 2.0), "dmma+dfma": e.fp64_peak(2, 2.0)}
+out = {"dmma": e.fp64_peak(0, 2.0), "dfma": e.fp64_peak(1, 2.0), "dmma+dfma": e.fp64_peak(2, 2.0),
+       "dmma_8warps_per_sm": e.fp64_peak(3, 1.0), "dmma_4warps_per_sm": e.fp64_peak(4, 1.0)}
 print(json.dumps(out))
