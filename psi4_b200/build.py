@@ -29,5 +29,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+INTS_LIB = os.path.join(HERE, "libb200ints.so")
+
+
+def build_ints(force: bool = False) -> str:
+    """Host-side integral front end (plain C, gcc + OpenMP)."""
+    src = os.path.join(CSRC, "ints.c")
+    if not force and os.path.exists(INTS_LIB) and os.path.getmtime(INTS_LIB) >= os.path.getmtime(src):
+        return INTS_LIB
+    subprocess.check_call(["gcc", "-O3", "-march=x86-64-v3", "-fopenmp", "-shared", "-fPIC", "-std=gnu11", "-o",
+                           INTS_LIB, src, "-lm"])
+    return INTS_LIB
+
+
 if __name__ == "__main__":
+    print(build_ints(force="--force" in sys.argv))
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
