@@ -62,6 +62,8 @@ def lib():
         L.oracle_last_timings.argtypes = [_dp]
         L.oracle_compute_D.argtypes = [_sz, ct.c_int, _dp, _dp, _dp]
         L.oracle_synth_fill.argtypes = [_sz, _sz, _sz, ct.c_uint64, _dp, _szp, _szp, _szp, _dp]
+        L.oracle_synth_rowblock.argtypes = [_sz, _sz, ct.c_uint64, _dp, ct.POINTER(ct.c_ubyte), _sz, _dp]
+        L.oracle_synth_dq.argtypes = [_sz, _sz, ct.c_uint64, _dp, ct.POINTER(ct.c_ubyte), _dp, _dp]
         rc = L.oracle_init(find_openblas().encode())
         if rc:
             raise RuntimeError(f"oracle_init failed rc={rc}")
@@ -128,6 +130,27 @@ def synth_fill(sp: Sparsity, q0: int, nq: int, seed: int, amp: np.ndarray) -> np
     lib().oracle_synth_fill(sp.nbf, q0, nq, ct.c_uint64(seed), _d(amp), _s(sp.fun_index), _s(sp.small_skips),
                             _s(sp.big_skips), _d(out))
     return out
+
+
+def synth_rowblock(keep, naux, seed, amp, m):
+    """Dense B[:, m, :] (naux, nbf) of the synthetic tensor, regenerated from the counter hash."""
+    keep = np.ascontiguousarray(keep, dtype=np.uint8)
+    amp = np.ascontiguousarray(amp, dtype=np.float64)
+    n = keep.shape[0]
+    out = np.empty((naux, n))
+    lib().oracle_synth_rowblock(n, naux, ct.c_uint64(seed), _d(amp), keep.ctypes.data_as(ct.POINTER(ct.c_ubyte)), m, _d(out))
+    return out
+
+
+def synth_dq(keep, naux, seed, amp, D):
+    """d[q] = sum_mn B(q,m,n) D[m,n] over the whole synthetic tensor (one pass over naux*nbf^2 hash evaluations)."""
+    keep = np.ascontiguousarray(keep, dtype=np.uint8)
+    amp = np.ascontiguousarray(amp, dtype=np.float64)
+    D = np.ascontiguousarray(D, dtype=np.float64)
+    d = np.empty(naux)
+    lib().oracle_synth_dq(keep.shape[0], naux, ct.c_uint64(seed), _d(amp), keep.ctypes.data_as(ct.POINTER(ct.c_ubyte)),
+                          _d(D), _d(d))
+    return d
 
 
 def _ptrs(arrs):
