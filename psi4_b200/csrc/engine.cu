@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/b200jk.h"
@@ -75,7 +76,8 @@ struct Phase {
 struct Shard {
     int dev = 0;
     int q0 = 0, q1 = 0, nq = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;  // compute stream
+    cudaStream_t copy = nullptr;    // copy stream: D upload and K download overlap the kernels
     double* tensor[3] = {nullptr, nullptr, nullptr};
     CUtensorMap* d_amaps[3] = {nullptr, nullptr, nullptr};  // per-row-block TMA descriptors of each tensor
     int nsm = 148;
@@ -561,21 +563,44 @@ int ensure_work(b200jk* h, Shard& s, const Task& t, int* qc_out) {
     return 0;
 }
 
-// All kernels of one build on one shard.  Operands are device pointers on s.dev.
-int run_device(b200jk* h, Shard& s, const Task& t, const double* const* dCl, const double* const* dCr,
-               const double* const* dD, int qc) {
+// Device pointers of the three output groups inside s.out: [J x nmat | K x nmat | wK x nmat] (tasked ones only).
+struct OutLayout {
+    size_t offJ, offK, offW, countJ, countKW, total;
+};
+OutLayout out_layout(const Task& t) {
+    OutLayout o;
+    o.offJ = 0;
+    o.countJ = (size_t)(t.do_J ? t.nmat : 0) * t.n2;
+    o.offK = o.countJ;
+    o.offW = o.offK + (size_t)(t.do_K ? t.nmat : 0) * t.n2;
+    o.countKW = (size_t)((t.do_K ? t.nmat : 0) + (t.do_wK ? t.nmat : 0)) * t.n2;
+    o.total = o.countJ + o.countKW;
+    return o;
+}
+
+// The J sweeps of one build on one shard (K1, K2 per density).
+int run_device_J(b200jk* h, Shard& s, const Task& t, const double* const* dD) {
+    if (!t.do_J) return 0;
+    CK(cudaSetDevice(s.dev));
+    const OutLayout ol = out_layout(t);
+    CK(cudaMemsetAsync(s.out + ol.offJ, 0, ol.countJ * sizeof(double), s.stream));
+    int rc;
+    PhaseScope ps(s, 0);
+    for (int i = 0; i < t.nmat; i++)
+        if ((rc = run_j(h, s, dD[i], t.lr, s.out + ol.offJ + i * t.n2))) return rc;
+    return 0;
+}
+
+// The K and wK builds of one shard (K3, K4 per density and Q chunk).
+int run_device_K(b200jk* h, Shard& s, const Task& t, const double* const* dCl, const double* const* dCr, int qc) {
+    if (!t.do_K && !t.do_wK) return 0;
     CK(cudaSetDevice(s.dev));
     const size_t N = h->nbf, n2 = t.n2;
-    double* outJ = s.out;
-    double* outK = s.out + (size_t)(t.do_J ? t.nmat : 0) * n2;
-    double* outW = outK + (size_t)(t.do_K ? t.nmat : 0) * n2;
-    CK(cudaMemsetAsync(s.out, 0, (size_t)t.nmat * t.nprod * n2 * sizeof(double), s.stream));
+    const OutLayout ol = out_layout(t);
+    double* outK = s.out + ol.offK;
+    double* outW = s.out + ol.offW;
+    CK(cudaMemsetAsync(s.out + ol.offK, 0, ol.countKW * sizeof(double), s.stream));
     int rc;
-    if (t.do_J) {
-        PhaseScope ps(s, 0);
-        for (int i = 0; i < t.nmat; i++)
-            if ((rc = run_j(h, s, dD[i], t.lr, outJ + i * n2))) return rc;
-    }
     const int ldc = round_up((int)N, 4);
     for (int pass = 0; pass < 2; pass++) {
         bool wk = pass == 1;
@@ -666,17 +691,44 @@ int collect_stats(b200jk* h) {
     return 0;
 }
 
-int allreduce(b200jk* h, size_t count) {
+// Sum `count` doubles at s.out + off over all Q shards.  use_copy: issue on the copy stream (K results are
+// reduced and sent home while the J sweeps still run on the compute stream).
+int allreduce(b200jk* h, size_t off, size_t count, bool use_copy) {
     bool multi = h->sh.size() > 1 || (h->rank_mode && h->world > 1);
-    if (!multi) return 0;
+    if (!multi || !count) return 0;
     if (h->sh.size() > 1) NK(g_nccl.GroupStart());
     for (auto& s : h->sh) {
         CK(cudaSetDevice(s.dev));
-        PhaseScope ps(s, 3);
-        NK(g_nccl.AllReduce(s.out, s.out, count, kNcclDouble, kNcclSum, s.comm, s.stream));
+        cudaStream_t st = use_copy ? s.copy : s.stream;
+        Phase ph;
+        ph.tag = 3;
+        ph.a = get_event(s);
+        ph.b = get_event(s);
+        CK(cudaEventRecord(ph.a, st));
+        NK(g_nccl.AllReduce(s.out + off, s.out + off, count, kNcclDouble, kNcclSum, s.comm, st));
+        CK(cudaEventRecord(ph.b, st));
+        s.phases.push_back(ph);
     }
     if (h->sh.size() > 1) NK(g_nccl.GroupEnd());
     return 0;
+}
+
+// memcpy split over a few threads: the staging copies of D / J / K (tens of MB) otherwise cost more than the PCIe hop.
+void par_memcpy(void* dst, const void* src, size_t bytes) {
+    const size_t chunk = (size_t)4 << 20;
+    if (bytes < 2 * chunk) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    int nt = (int)std::min<size_t>(4, bytes / chunk);
+    std::vector<std::thread> th;
+    size_t per = (bytes / nt + 63) & ~(size_t)63;
+    for (int i = 1; i < nt; i++) {
+        size_t a = per * i, b = std::min(bytes, per * (i + 1));
+        if (a < b) th.emplace_back([=] { memcpy((char*)dst + a, (const char*)src + a, b - a); });
+    }
+    memcpy(dst, src, std::min(per, bytes));
+    for (auto& x : th) x.join();
 }
 
 int check_compute_args(b200jk* h, int nmat, const int* nocc, bool do_J, bool do_K, bool do_wK) {
@@ -711,6 +763,7 @@ int setup_shards(b200jk* h, int n, const int* devs) {
         if (s.dev < 0 || s.dev >= ndev) return fail(h, B200JK_ERR_INVALID, "device %d out of range (%d visible)", s.dev, ndev);
         CK(cudaSetDevice(s.dev));
         CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking));
         CK(cudaDeviceGetAttribute(&s.nsm, cudaDevAttrMultiProcessorCount, s.dev));
     }
     return load_encode(h);
@@ -731,6 +784,7 @@ void free_shard(Shard& s) {
     for (auto e : s.evpool) cudaEventDestroy(e);
     if (s.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s.comm);
     if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.copy) cudaStreamDestroy(s.copy);
 }
 
 int alloc_tensor(b200jk* h, int which) {
@@ -1064,9 +1118,12 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
     for (size_t i = 0; i < h->sh.size(); i++)
         if ((rc = ensure_work(h, h->sh[i], t, &qc[i]))) return rc;
 
-    // total-time bracket
-    std::vector<Phase> total(h->sh.size());
-    for (size_t i = 0; i < h->sh.size(); i++) {
+    // Order of one build: C up -> K/wK kernels -> [D up on the copy stream meanwhile] -> J sweeps; the K results are
+    // all-reduced and brought home on the copy stream while J runs.  Event pairs bracket every phase.
+    const OutLayout ol = out_layout(t);
+    const size_t nsh = h->sh.size();
+    std::vector<Phase> total(nsh);
+    for (size_t i = 0; i < nsh; i++) {
         Shard& s = h->sh[i];
         CK(cudaSetDevice(s.dev));
         total[i].tag = 6;
@@ -1075,26 +1132,29 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
         CK(cudaEventRecord(total[i].a, s.stream));
     }
 
-    std::vector<std::vector<const double*>> dCl(h->sh.size()), dCr(h->sh.size()), dD(h->sh.size());
+    std::vector<std::vector<const double*>> dCl(nsh), dCr(nsh), dD(nsh);
     const bool needC = do_K || do_wK;
+    size_t c_doubles = 0, d_doubles = do_J ? (size_t)nmat * n2 : 0;
+    if (needC)
+        for (int i = 0; i < nmat; i++) c_doubles += N * (size_t)nocc[i] * (t.lr ? 1 : 2);
+    std::vector<size_t> offCl(nmat, 0), offCr(nmat, 0);
     if (host_ops) {
-        // stage C (first: the K build can start while D is still in flight) then D through pinned memory
-        size_t in_doubles = 0;
-        for (int i = 0; i < nmat; i++) {
-            if (needC) in_doubles += N * (size_t)nocc[i] * (t.lr ? 1 : 2);
-            if (do_J) in_doubles += n2;
-        }
-        in_doubles = std::max<size_t>(in_doubles, 1);
+        size_t in_doubles = std::max<size_t>(c_doubles + d_doubles, 1);
         if (in_doubles > h->pin_in_cap) {
             if (h->pin_in) CK(cudaFreeHost(h->pin_in));
             h->pin_in = nullptr;
             CK(cudaHostAlloc((void**)&h->pin_in, in_doubles * 8, cudaHostAllocPortable));
             h->pin_in_cap = in_doubles;
         }
-        std::vector<size_t> offCl(nmat), offCr(nmat), offD(nmat);
+        if (ol.total > h->pin_out_cap) {
+            if (h->pin_out) CK(cudaFreeHost(h->pin_out));
+            h->pin_out = nullptr;
+            CK(cudaHostAlloc((void**)&h->pin_out, ol.total * 8, cudaHostAllocPortable));
+            h->pin_out_cap = ol.total;
+        }
         size_t off = 0;
-        for (int i = 0; i < nmat; i++) {
-            if (needC) {
+        if (needC) {
+            for (int i = 0; i < nmat; i++) {
                 size_t c = N * (size_t)nocc[i];
                 offCl[i] = off;
                 if (c) memcpy(h->pin_in + off, Cl[i], c * 8);
@@ -1106,31 +1166,21 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
                 }
             }
         }
-        size_t c_end = off;
-        for (int i = 0; i < nmat; i++) {
-            if (do_J) {
-                offD[i] = off;
-                memcpy(h->pin_in + off, D[i], n2 * 8);
-                off += n2;
-            }
-        }
-        for (size_t si = 0; si < h->sh.size(); si++) {
+        for (size_t si = 0; si < nsh; si++) {
             Shard& s = h->sh[si];
             CK(cudaSetDevice(s.dev));
             if ((rc = grow(h, &s.in, &s.in_cap, in_doubles))) return rc;
-            {
+            if (c_doubles) {
                 PhaseScope ps(s, 4);
-                if (c_end) CK(cudaMemcpyAsync(s.in, h->pin_in, c_end * 8, cudaMemcpyHostToDevice, s.stream));
-                if (off > c_end)
-                    CK(cudaMemcpyAsync(s.in + c_end, h->pin_in + c_end, (off - c_end) * 8, cudaMemcpyHostToDevice, s.stream));
+                CK(cudaMemcpyAsync(s.in, h->pin_in, c_doubles * 8, cudaMemcpyHostToDevice, s.stream));
             }
-            dCl[si].resize(nmat);
-            dCr[si].resize(nmat);
-            dD[si].resize(nmat);
+            dCl[si].assign(nmat, nullptr);
+            dCr[si].assign(nmat, nullptr);
+            dD[si].assign(nmat, nullptr);
             for (int i = 0; i < nmat; i++) {
-                dCl[si][i] = needC ? s.in + offCl[i] : nullptr;
-                dCr[si][i] = (needC && !t.lr) ? s.in + offCr[i] : nullptr;
-                dD[si][i] = do_J ? s.in + offD[i] : nullptr;
+                if (needC) dCl[si][i] = s.in + offCl[i];
+                if (needC && !t.lr) dCr[si][i] = s.in + offCr[i];
+                if (do_J) dD[si][i] = s.in + c_doubles + (size_t)i * n2;
             }
         }
     } else {
@@ -1144,28 +1194,80 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
         }
     }
 
-    for (size_t si = 0; si < h->sh.size(); si++)
-        if ((rc = run_device(h, h->sh[si], t, dCl[si].data(), dCr[si].data(), dD[si].data(), qc[si]))) return rc;
+    // K / wK kernels
+    std::vector<cudaEvent_t> evK(nsh), evD(nsh);
+    for (size_t si = 0; si < nsh; si++) {
+        Shard& s = h->sh[si];
+        if ((rc = run_device_K(h, s, t, dCl[si].data(), dCr[si].data(), qc[si]))) return rc;
+        CK(cudaSetDevice(s.dev));
+        evK[si] = get_event(s);
+        evD[si] = get_event(s);
+        CK(cudaEventRecord(evK[si], s.stream));
+    }
 
-    size_t out_count = (size_t)nmat * t.nprod * n2;
-    if ((rc = allreduce(h, out_count))) return rc;
-
-    // results: shard 0 holds the reduced sums
-    Shard& s0 = h->sh[0];
-    CK(cudaSetDevice(s0.dev));
-    double* const* outs[3] = {do_J ? J : nullptr, do_K ? K : nullptr, do_wK ? wK : nullptr};
-    if (host_ops) {
-        if (out_count > h->pin_out_cap) {
-            if (h->pin_out) CK(cudaFreeHost(h->pin_out));
-            h->pin_out = nullptr;
-            CK(cudaHostAlloc((void**)&h->pin_out, out_count * 8, cudaHostAllocPortable));
-            h->pin_out_cap = out_count;
+    // D goes up on the copy stream while K computes
+    if (host_ops && do_J) {
+        for (int i = 0; i < nmat; i++) par_memcpy(h->pin_in + c_doubles + (size_t)i * n2, D[i], n2 * 8);
+        for (size_t si = 0; si < nsh; si++) {
+            Shard& s = h->sh[si];
+            CK(cudaSetDevice(s.dev));
+            Phase ph;
+            ph.tag = 4;
+            ph.a = get_event(s);
+            ph.b = get_event(s);
+            CK(cudaEventRecord(ph.a, s.copy));
+            CK(cudaMemcpyAsync(s.in + c_doubles, h->pin_in + c_doubles, d_doubles * 8, cudaMemcpyHostToDevice, s.copy));
+            CK(cudaEventRecord(ph.b, s.copy));
+            s.phases.push_back(ph);
+            CK(cudaEventRecord(evD[si], s.copy));
+            CK(cudaStreamWaitEvent(s.stream, evD[si], 0));
         }
-        {
+    }
+
+    // J sweeps
+    for (size_t si = 0; si < nsh; si++)
+        if ((rc = run_device_J(h, h->sh[si], t, dD[si].data()))) return rc;
+
+    // K results: reduce + download on the copy stream (overlaps the J sweeps); J results follow on the compute stream
+    Shard& s0 = h->sh[0];
+    double* const* outs[3] = {do_J ? J : nullptr, do_K ? K : nullptr, do_wK ? wK : nullptr};
+    cudaEvent_t evKhome = nullptr;
+    if (host_ops) {
+        for (size_t si = 0; si < nsh; si++) {
+            CK(cudaSetDevice(h->sh[si].dev));
+            CK(cudaStreamWaitEvent(h->sh[si].copy, evK[si], 0));
+        }
+        if ((rc = allreduce(h, ol.offK, ol.countKW, true))) return rc;
+        CK(cudaSetDevice(s0.dev));
+        if (ol.countKW) {
+            Phase ph;
+            ph.tag = 5;
+            ph.a = get_event(s0);
+            ph.b = get_event(s0);
+            CK(cudaEventRecord(ph.a, s0.copy));
+            CK(cudaMemcpyAsync(h->pin_out + ol.offK, s0.out + ol.offK, ol.countKW * 8, cudaMemcpyDeviceToHost, s0.copy));
+            CK(cudaEventRecord(ph.b, s0.copy));
+            s0.phases.push_back(ph);
+        }
+        evKhome = get_event(s0);
+        CK(cudaEventRecord(evKhome, s0.copy));
+        if ((rc = allreduce(h, ol.offJ, ol.countJ, false))) return rc;
+        CK(cudaSetDevice(s0.dev));
+        if (ol.countJ) {
             PhaseScope ps(s0, 5);
-            CK(cudaMemcpyAsync(h->pin_out, s0.out, out_count * 8, cudaMemcpyDeviceToHost, s0.stream));
+            CK(cudaMemcpyAsync(h->pin_out + ol.offJ, s0.out + ol.offJ, ol.countJ * 8, cudaMemcpyDeviceToHost, s0.stream));
+        }
+        // every shard's compute stream also waits for its copy stream so `total` covers both
+        for (size_t si = 0; si < nsh; si++) {
+            Shard& s = h->sh[si];
+            CK(cudaSetDevice(s.dev));
+            cudaEvent_t e = get_event(s);
+            CK(cudaEventRecord(e, s.copy));
+            CK(cudaStreamWaitEvent(s.stream, e, 0));
         }
     } else {
+        if ((rc = allreduce(h, 0, ol.total, false))) return rc;
+        CK(cudaSetDevice(s0.dev));
         size_t off = 0;
         for (int pr = 0; pr < 3; pr++) {
             if (!outs[pr]) continue;
@@ -1173,23 +1275,29 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
                 CK(cudaMemcpyAsync(outs[pr][i], s0.out + off, n2 * 8, cudaMemcpyDeviceToDevice, s0.stream));
         }
     }
-    for (size_t i = 0; i < h->sh.size(); i++) {
+    for (size_t i = 0; i < nsh; i++) {
         Shard& s = h->sh[i];
         CK(cudaSetDevice(s.dev));
         CK(cudaEventRecord(total[i].b, s.stream));
         s.phases.push_back(total[i]);
     }
+    if (host_ops) {
+        // K / wK leave the staging buffer while the GPU is still busy with J
+        CK(cudaSetDevice(s0.dev));
+        CK(cudaEventSynchronize(evKhome));
+        size_t off = ol.offK;
+        for (int pr = 1; pr < 3; pr++) {
+            if (!outs[pr]) continue;
+            for (int i = 0; i < nmat; i++, off += n2) par_memcpy(outs[pr][i], h->pin_out + off, n2 * 8);
+        }
+    }
     for (auto& s : h->sh) {
         CK(cudaSetDevice(s.dev));
         CK(cudaStreamSynchronize(s.stream));
+        CK(cudaStreamSynchronize(s.copy));
     }
-    if (host_ops) {
-        size_t off = 0;
-        for (int pr = 0; pr < 3; pr++) {
-            if (!outs[pr]) continue;
-            for (int i = 0; i < nmat; i++, off += n2) memcpy(outs[pr][i], h->pin_out + off, n2 * 8);
-        }
-    }
+    if (host_ops && do_J)
+        for (int i = 0; i < nmat; i++) par_memcpy(J[i], h->pin_out + ol.offJ + (size_t)i * n2, n2 * 8);
     account_work(h, t);
     collect_stats(h);
     h->stats.hbm_work_bytes = 0;

@@ -203,7 +203,8 @@ class MemDFJK(JK):
             self.J_, self.K_, self.wK_ = [], [], []
             return
         try:
-            J, K, wK = self.engine.compute(self._Cl, self._Cr, self.D_, self.do_J_, self.do_K_, self.do_wK_)
+            J, K, wK = self.engine.compute(self._Cl, self._Cr, self.D_, self.do_J_, self.do_K_, self.do_wK_,
+                                           reuse_outputs=True)
         except _lib.B200JKError as e:
             raise PsiException(str(e)) from e
         n = self.nbf_
