@@ -367,6 +367,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
 // ---------------------------------------------------------------------------------------------
 struct KgemmWsParams {
     int nbf, kdim, klen, ntiles, nitems;
+    int symmetric;      // T2 == T1: only tiles with tn >= tm are listed; diagonal tiles skip their lower half
     const int2* tiles;  // [ntiles] (tm, tn)
     int* counter;
     double* ws;         // [nsplit][ntiles][128*128]
@@ -438,7 +439,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         const int ke = min(p.kdim, kb + p.klen);
         const int nkt = (ke - kb + BK - 1) / BK;
         const int mbv = max(0, min(4, (p.nbf - (tl.x * BM + wm * 32) + 7) / 8));
-        const int nbv = max(0, min(NB, (p.nbf - (tl.y * BN + wn * 8 * NB) + 7) / 8));
+        int nbv = max(0, min(NB, (p.nbf - (tl.y * BN + wn * 8 * NB) + 7) / 8));
+        // diagonal tile of a symmetric product: rows 64..127 x cols 0..63 lie strictly below the diagonal and are
+        // mirrored by the reduction, so the two warps that own them issue no DMMAs
+        if (p.symmetric && tl.x == tl.y && wn == 0 && wm >= 2) nbv = 0;
         double acc[4][NB][2];
 #pragma unroll
         for (int a = 0; a < 4; a++)
@@ -479,8 +483,16 @@ __global__ void kgemm_reduce_list_kernel(const double* __restrict__ ws, int nspl
         if (m < nbf && n < nbf) {
             double s = 0.0;
             for (int sp = 0; sp < nsplit; sp++) s += ws[((size_t)sp * ntiles + tile) * (BM * 128) + e];
-            K[(size_t)m * nbf + n] += s;
-            if (symmetric && tl.y > tl.x) K[(size_t)n * nbf + m] += s;
+            if (symmetric && tl.y == tl.x) {
+                // diagonal tile: the upper triangle is authoritative, the lower one is its mirror
+                if (c >= r) {
+                    K[(size_t)m * nbf + n] += s;
+                    if (c > r) K[(size_t)n * nbf + m] += s;
+                }
+            } else {
+                K[(size_t)m * nbf + n] += s;
+                if (symmetric) K[(size_t)n * nbf + m] += s;
+            }
         }
     }
 }

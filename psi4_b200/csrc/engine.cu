@@ -346,6 +346,7 @@ int run_kgemm_ws(b200jk* h, Shard& s, const double* T1, const double* T2, int kd
     p.klen = klen;
     p.ntiles = ntiles;
     p.nitems = ntiles * nsplit;
+    p.symmetric = symmetric ? 1 : 0;
     p.tiles = tiles;
     p.counter = s.d_counter;
     p.ws = s.ws;

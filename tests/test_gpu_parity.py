@@ -261,3 +261,71 @@ def test_error_paths():
         jk.compute()  # jk.cc:612-615 zip mismatch
     with pytest.raises(PsiException):
         jk.set_wcombine(True)
+
+
+@pytest.mark.parametrize("nocc", [1, 2, 7, 8, 9, 63, 64, 65, 127, 128, 129, 200])
+def test_nocc_sweep_tile_edges(oracle, nocc):
+    """Every orbital-tile shape of the half transform (1..8 DMMA column blocks, 1 and 2 i-tiles, ragged last block)
+    and K-GEMM k lengths that are not multiples of the stage depth."""
+    from psi4_b200 import Engine
+
+    rng = np.random.default_rng(1000 + nocc)
+    n, a = 150, 37 + (nocc % 5)
+    keep = random_mask(rng, n, 0.7) if nocc % 2 else np.ones((n, n), bool)
+    sp, d, B, P = make(oracle, rng, n, a, keep, 0.1)
+    C = [rng.standard_normal((n, nocc))]
+    D = [C[0] @ C[0].T]
+    e = Engine(1)
+    e.set_layout(n, a, d.small_skips_, d.big_skips_, d.schwarz_fun_index_)
+    e.upload(0, P)
+    J, K, _ = e.compute(C, None, D)
+    Jo, Ko, _, _ = oracle.build_JK(sp, P, C, D=D)
+    scale = max(1.0, np.abs(Ko[0]).max())
+    assert np.abs(J[0] - Jo[0]).max() < TOL * max(1.0, np.abs(Jo[0]).max())
+    assert np.abs(K[0] - Ko[0]).max() < TOL * scale
+    e.close()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_shapes(oracle, seed):
+    """Randomised shapes: nbf around the 128-row tile edges, naux below / across one q tile, random screening,
+    symmetric and general paths, 1-3 densities with ragged nocc."""
+    from psi4_b200 import Engine
+
+    rng = np.random.default_rng(seed)
+    n = int(rng.choice([5, 31, 127, 128, 129, 200, 257]))
+    a = int(rng.choice([1, 3, 64, 127, 128, 129, 300]))
+    dens = float(rng.choice([1.0, 0.8, 0.3, 0.05]))
+    lr = bool(rng.integers(2))
+    keep = random_mask(rng, n, dens)
+    sp, d, B, P = make(oracle, rng, n, a, keep, 0.2)
+    nmat = int(rng.integers(1, 4))
+    noccs = [int(rng.integers(0, min(n, 40) + 1)) for _ in range(nmat)]
+    Cl = [rng.standard_normal((n, o)) for o in noccs]
+    Cr = None if lr else [rng.standard_normal((n, o)) for o in noccs]
+    D = [x @ (x if lr else y).T for x, y in zip(Cl, Cl if lr else Cr)]
+    e = Engine(1)
+    e.set_layout(n, a, d.small_skips_, d.big_skips_, d.schwarz_fun_index_)
+    e.upload(0, P)
+    J, K, _ = e.compute(Cl, Cr, D)
+    Jo, Ko, _, _ = oracle.build_JK(sp, P, Cl, Cr, D=D)
+    for i in range(nmat):
+        assert np.abs(J[i] - Jo[i]).max() < TOL * max(1.0, np.abs(Jo[i]).max()), (n, a, dens, lr, noccs)
+        assert np.abs(K[i] - Ko[i]).max() < TOL * max(1.0, np.abs(Ko[i]).max()), (n, a, dens, lr, noccs)
+    e.close()
+
+
+def test_oom_is_an_error_not_a_fallback():
+    """In-core only: a tensor that does not fit in HBM fails loudly (mirrors SCF_SUBTYPE=INCORE throwing,
+    dfhelper.cc:259-262); nothing spills to the host."""
+    from psi4_b200 import B200JKError, DFHelper, Engine
+
+    n, a = 2048, 20000  # 2048^2 * 20000 * 8 B = 671 GB
+    d = DFHelper(n, a)
+    d.prepare_sparsity(keep=np.ones((n, n), bool))
+    e = Engine(1)
+    e.set_layout(n, a, d.small_skips_, d.big_skips_, d.schwarz_fun_index_)
+    with pytest.raises(B200JKError) as ei:
+        e.fill_synthetic(0, 1, np.ones((n, n)))
+    assert ei.value.code == 3  # B200JK_ERR_OOM
+    e.close()
