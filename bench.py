@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-slice", type=int, default=0, help="Q rows in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-probes", action="store_true", help="no FP64 ceiling probes (ncu launch lists); roofline.peak = last recorded")
     ap.add_argument("--nonsymmetric", action="store_true", help="C_right != C_left (general path)")
     return ap.parse_args()
 
@@ -205,8 +206,8 @@ def main():
     dK = [eng.dev_alloc(n2b) for _ in range(nmat)]
     noccs = [nocc] * nmat
 
-    pk_dmma = eng.fp64_peak(0, 1.5) if rank == 0 else None
-    pk_dfma = eng.fp64_peak(1, 0.5) if rank == 0 else None
+    pk_dmma = eng.fp64_peak(0, 0.0 if args.skip_probes else 1.5) if rank == 0 else None
+    pk_dfma = eng.fp64_peak(1, 0.0 if args.skip_probes else 0.5) if rank == 0 else None
     # kernels timed inside a long step -> sustained ceiling (B200_PROFILING.md); the burst figure is reported too
     peak_dmma = pk_dmma["sustained_tflops"] if pk_dmma else 0.0
 

@@ -38,6 +38,14 @@ constexpr int WS_PRODUCER_THREADS = 32 * WS_PRODUCER_WARPS;
 constexpr int WS_THREADS = 32 * (WS_CONSUMER_WARPS + WS_PRODUCER_WARPS);
 constexpr int WS_ROW_BYTES = 128;            // BK doubles
 constexpr int WS_A_STAGE = BM * WS_ROW_BYTES;  // 16 KB
+// The 16 row blocks (8 rows each) of a 128-row tile are dealt round-robin to the four M warps (= the four SM
+// sub-partitions): block b belongs to warp b % 4, so a ragged tile (e.g. 80 live rows on the last q tile of a
+// Q shard) still loads all four DMMA pipes evenly instead of leaving two of them idle.
+constexpr int WS_A_MB_STRIDE = 32 * WS_ROW_BYTES;  // warp's next row block is 4 blocks = 32 rows further
+__device__ __forceinline__ int live_row_blocks(int rows_live, int wm) {
+    int nblk = (min(max(rows_live, 0), BM) + 7) >> 3;  // live 8-row blocks in the tile
+    return max(0, min(4, (nblk - wm + 3) >> 2));      // those with index = wm (mod 4)
+}
 
 template <int NB>
 constexpr size_t ws_smem_bytes() {
@@ -99,7 +107,7 @@ __device__ __forceinline__ void mma_stage_swz(const uint8_t* __restrict__ a_row,
     for (int ks = 0; ks < 4; ks++) {
         double a[4], b[NB];
 #pragma unroll
-        for (int mb = 0; mb < 4; mb++) a[mb] = *reinterpret_cast<const double*>(a_row + mb * 8 * WS_ROW_BYTES + off[ks]);
+        for (int mb = 0; mb < 4; mb++) a[mb] = *reinterpret_cast<const double*>(a_row + mb * WS_A_MB_STRIDE + off[ks]);
 #pragma unroll
         for (int nb = 0; nb < NB; nb++) b[nb] = *reinterpret_cast<const double*>(b_row + nb * 8 * WS_ROW_BYTES + off[ks]);
         if (FULL) {
@@ -120,47 +128,50 @@ __device__ __forceinline__ void mma_stage_swz(const uint8_t* __restrict__ a_row,
     }
 }
 
-// Same stage with all four row blocks live and exactly LIVE (compile-time) column blocks: an unpredicated
-// DMMA stream for ragged nocc tiles (the predicated generic path costs a WARPSYNC + branch per DMMA).
-template <int NB, int LIVE>
-__device__ __forceinline__ void mma_stage_live(const uint8_t* __restrict__ a_row, const uint8_t* __restrict__ b_row,
-                                               const int (&off)[4], double (&acc)[4][NB][2]) {
+// Unpredicated stage for a warp with exactly MLIVE live 8-row blocks and LIVE live 8-column blocks, both compile-time
+// (a predicated mma.sync costs a WARPSYNC + branch per DMMA and one slow warp gates the whole stage ring).
+template <int NB, int MLIVE, int LIVE>
+__device__ __forceinline__ void mma_stage_ml(const uint8_t* __restrict__ a_row, const uint8_t* __restrict__ b_row,
+                                             const int (&off)[4], double (&acc)[4][NB][2]) {
 #pragma unroll
     for (int ks = 0; ks < 4; ks++) {
-        double a[4], b[LIVE];
+        double a[MLIVE], b[LIVE];
 #pragma unroll
-        for (int mb = 0; mb < 4; mb++) a[mb] = *reinterpret_cast<const double*>(a_row + mb * 8 * WS_ROW_BYTES + off[ks]);
+        for (int mb = 0; mb < MLIVE; mb++) a[mb] = *reinterpret_cast<const double*>(a_row + mb * WS_A_MB_STRIDE + off[ks]);
 #pragma unroll
         for (int nb = 0; nb < LIVE; nb++) b[nb] = *reinterpret_cast<const double*>(b_row + nb * 8 * WS_ROW_BYTES + off[ks]);
 #pragma unroll
-        for (int mb = 0; mb < 4; mb++)
+        for (int mb = 0; mb < MLIVE; mb++)
 #pragma unroll
             for (int nb = 0; nb < LIVE; nb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
     }
 }
-template <int NB, int LIVE>
-struct StageDispatch {
+template <int NB, int MLIVE, int LIVE>
+struct StageDispatchN {
     static __device__ __forceinline__ void run(const uint8_t* a_row, const uint8_t* b_row, const int (&off)[4],
                                                double (&acc)[4][NB][2], int nbv) {
         if (nbv == LIVE)
-            mma_stage_live<NB, LIVE>(a_row, b_row, off, acc);
+            mma_stage_ml<NB, MLIVE, LIVE>(a_row, b_row, off, acc);
         else
-            StageDispatch<NB, LIVE - 1>::run(a_row, b_row, off, acc, nbv);
+            StageDispatchN<NB, MLIVE, LIVE - 1>::run(a_row, b_row, off, acc, nbv);
     }
 };
-template <int NB>
-struct StageDispatch<NB, 0> {
+template <int NB, int MLIVE>
+struct StageDispatchN<NB, MLIVE, 0> {
     static __device__ __forceinline__ void run(const uint8_t*, const uint8_t*, const int (&)[4], double (&)[4][NB][2], int) {}
 };
-// mbv / nbv are warp-uniform: all-rows-live tiles take a specialised unpredicated stream, the last q tile of a
-// shard (mbv < 4, one item in ~38) takes the predicated generic path.
+// mbv / nbv are warp-uniform: every (rows, columns) combination of live blocks has its own unpredicated stream.
 template <int NB>
 __device__ __forceinline__ void mma_stage_any(const uint8_t* a_row, const uint8_t* b_row, const int (&off)[4],
                                               double (&acc)[4][NB][2], int mbv, int nbv) {
     if (mbv == 4)
-        StageDispatch<NB, NB>::run(a_row, b_row, off, acc, nbv);
-    else
-        mma_stage_swz<NB, false>(a_row, b_row, off, acc, mbv, nbv);
+        StageDispatchN<NB, 4, NB>::run(a_row, b_row, off, acc, nbv);
+    else if (mbv == 3)
+        StageDispatchN<NB, 3, NB>::run(a_row, b_row, off, acc, nbv);
+    else if (mbv == 2)
+        StageDispatchN<NB, 2, NB>::run(a_row, b_row, off, acc, nbv);
+    else if (mbv == 1)
+        StageDispatchN<NB, 1, NB>::run(a_row, b_row, off, acc, nbv);
 }
 
 struct WsCarve {
@@ -308,7 +319,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
     int off[4];
 #pragma unroll
     for (int ks = 0; ks < 4; ks++) off[ks] = (((ks + 4 * (t >> 1)) ^ gq) << 4) + ((t & 1) << 3);
-    const int a_row0 = (wm * 32 + gq) * WS_ROW_BYTES;
+    const int a_row0 = (wm * 8 + gq) * WS_ROW_BYTES;  // row blocks interleaved over the four M warps
     const int b_row0 = (wn * 8 * NB + gq) * WS_ROW_BYTES;
     uint32_t g = 0;
     for (;;) {
@@ -323,7 +334,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         const int nkt = (K + BK - 1) / BK;
         const int q0 = qt * BM, i0 = it * p.iw;
         const int icols = min(p.iw, p.o - i0);
-        const int mbv = max(0, min(4, (p.qc - (q0 + wm * 32) + 7) / 8));
+        const int mbv = live_row_blocks(p.qc - q0, wm);
         const int nbv = max(0, min(NB, (icols - wn * 8 * NB + 7) / 8));
         double acc[4][NB][2];
 #pragma unroll
@@ -346,7 +357,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         double* Tm = p.T + (size_t)m * p.qc * p.op;
 #pragma unroll
         for (int mb = 0; mb < 4; mb++) {
-            int q = q0 + wm * 32 + mb * 8 + gq;
+            int q = q0 + mb * 32 + wm * 8 + gq;
             if (q < p.qc) {
 #pragma unroll
                 for (int nb = 0; nb < NB; nb++) {
@@ -426,7 +437,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
     int off[4];
 #pragma unroll
     for (int ks = 0; ks < 4; ks++) off[ks] = (((ks + 4 * (t >> 1)) ^ gq) << 4) + ((t & 1) << 3);
-    const int a_row0 = (wm * 32 + gq) * WS_ROW_BYTES;
+    const int a_row0 = (wm * 8 + gq) * WS_ROW_BYTES;  // row blocks interleaved over the four M warps
     const int b_row0 = (wn * 8 * NB + gq) * WS_ROW_BYTES;
     uint32_t g = 0;
     for (;;) {
@@ -438,11 +449,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         const int kb = (w / p.ntiles) * p.klen;
         const int ke = min(p.kdim, kb + p.klen);
         const int nkt = (ke - kb + BK - 1) / BK;
-        const int mbv = max(0, min(4, (p.nbf - (tl.x * BM + wm * 32) + 7) / 8));
+        const int mbv = live_row_blocks(p.nbf - tl.x * BM, wm);
         int nbv = max(0, min(NB, (p.nbf - (tl.y * BN + wn * 8 * NB) + 7) / 8));
-        // diagonal tile of a symmetric product: rows 64..127 x cols 0..63 lie strictly below the diagonal and are
-        // mirrored by the reduction, so the two warps that own them issue no DMMAs
-        if (p.symmetric && tl.x == tl.y && wn == 0 && wm >= 2) nbv = 0;
+        // (diagonal tiles of a symmetric product are computed whole; the reduction keeps their upper triangle)
         double acc[4][NB][2];
 #pragma unroll
         for (int a = 0; a < 4; a++)
@@ -462,7 +471,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         double* wsp = p.ws + (size_t)w * (BM * BN);
 #pragma unroll
         for (int mb = 0; mb < 4; mb++) {
-            int r = wm * 32 + mb * 8 + gq;
+            int r = mb * 32 + wm * 8 + gq;
 #pragma unroll
             for (int nb = 0; nb < NB; nb++) {
                 int c = wn * 8 * NB + nb * 8 + t * 2;
