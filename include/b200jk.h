@@ -86,6 +86,23 @@ int b200jk_upload(b200jk_t* h, int which, const double* host_pQq);
  * at Ppq_ + big_skips[m0]. */
 int b200jk_upload_rows(b200jk_t* h, int which, size_t m0, size_t m1, const double* host_rows);
 
+/* ---- on-device fitting --------------------------------------------------------
+ * Moves DFHelper::contract_metric_AO_core_symm (dfhelper.cc:1653-1678) to the GPU: psi4 keeps computing the
+ * UNFITTED integrals on the CPU (compute_sparse_pQq_blocking_p_symm, :1284-1347) and hands each block over instead of
+ * running naux DGEMMs per basis function itself; the host never holds the fitted tensor and uploads half the bytes.
+ *
+ * b200jk_set_metric: naux x naux row-major metric power that prepare_AO_core contracts with (metp, :560-566):
+ *   J^-1/2 for Ppq_, J^-1 for m1Ppq_ (:642-650).  NULL = no contraction (wPpq_, :688-692: plain scatter + mirror).
+ *   Each Q shard keeps only its rows.
+ * b200jk_fit_rows: rows m in [m0, m1) of the symmetric-packed unfitted buffer exactly as psi4's Mp holds them:
+ *   host_sym[symm_big_skips[m] - symm_big_skips[m0] + Q*mi(m) + (f(m,n) - f(m,m))],  n >= m kept, mi(m) = symm_small_skips[m]
+ *   (:1338-1340).  Computes Ppq[m][Q][n>=m] = sum_R metric[Q,R] (R|mn) and the mirror copy B(Q,n,m) = B(Q,m,n)
+ *   (:1666-1677).  The block with m1 == nbf completes the tensor.  The pair mask must be symmetric. */
+int b200jk_set_metric(b200jk_t* h, const double* metric);
+int b200jk_fit_rows(b200jk_t* h, int which, size_t m0, size_t m1, const double* host_sym);
+/* device time (ms) and flops of the metric contraction accumulated since the fit_rows call with m0 == 0 */
+int b200jk_fit_stats(const b200jk_t* h, double* ms_gemm, double* flops);
+
 /* ---- the hot path ----------------------------------------------------------------------------- */
 
 /* DFHelper::build_JK (dfhelper.cc:3015-3043) + the zero()/hermitivitize() wrapper of

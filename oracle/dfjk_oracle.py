@@ -153,6 +153,30 @@ def synth_dq(keep, naux, seed, amp, D):
     return d
 
 
+def contract_metric_AO_core_symm(sp: Sparsity, Qpq_sym: np.ndarray, metp: np.ndarray, Ppq: np.ndarray | None = None,
+                                 begin: int = 0, end: int | None = None, nthreads=None) -> np.ndarray:
+    """dfhelper.cc:1653-1678 on the host: fitted + mirrored rows [begin, end] written into Ppq (allocated if None).
+    Qpq_sym is relative to symm_big_skips[begin]."""
+    L = lib()
+    if "_cm" not in L.__dict__:
+        L.oracle_contract_metric_AO_core_symm.argtypes = [_sz, _sz, ct.c_int, _szp, _szp, _szp, _szp, _szp, _szp, _dp, _dp,
+                                                          _dp, _sz, _sz]
+        L.oracle_contract_metric_AO_core_symm.restype = ct.c_int
+        L.__dict__["_cm"] = True
+    end = sp.nbf - 1 if end is None else end
+    if Ppq is None:
+        Ppq = np.zeros(sp.packed_size)
+    q = np.ascontiguousarray(Qpq_sym, dtype=np.float64)
+    m = np.ascontiguousarray(metp, dtype=np.float64)
+    rc = L.oracle_contract_metric_AO_core_symm(sp.nbf, sp.naux, nthreads or L.oracle_max_threads(), _s(sp.fun_index),
+                                               _s(sp.small_skips), _s(sp.big_skips), _s(sp.symm_small_skips),
+                                               _s(sp.symm_ignored_columns), _s(sp.symm_big_skips), _d(q), _d(Ppq), _d(m),
+                                               begin, end)
+    if rc:
+        raise RuntimeError("oracle_contract_metric_AO_core_symm failed")
+    return Ppq
+
+
 def _ptrs(arrs):
     return (_dp * len(arrs))(*[_d(a) for a in arrs])
 

@@ -481,6 +481,117 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fitting GEMM (DFHelper::contract_metric_AO_core_symm, dfhelper.cc:1653-1678):
+//   F[q, j] = sum_R Met[q, R] * U[j, R]      q in this shard's aux rows, j = staged (m, n>=m) pair column
+// Same persistent pipeline as the K GEMM (both operands by TMA, contraction index R contiguous), no split-K;
+// the epilogue scatters column j straight into the packed pQq tensor: dst_off[j] + q * dst_ld[j].
+// ---------------------------------------------------------------------------------------------
+struct FitGemmParams {
+    int nq, ncols, kdim;        // shard rows, staged pair columns, naux
+    int ntm, ntn, nitems;       // tiles along q, along j
+    const size_t* dst_off;      // [ncols] offset (doubles, from tensor base) of element (q=0) of column j
+    const int* dst_ld;          // [ncols] row pitch of the row-block column j belongs to
+    double* tensor;
+    int* counter;
+};
+
+__global__ void __launch_bounds__(WS_THREADS, 1)
+    fit_gemm_ws_kernel(const __grid_constant__ CUtensorMap metmap, const __grid_constant__ CUtensorMap umap, FitGemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int NB = 8, BN = 128;
+    constexpr int B_STAGE = BN * WS_ROW_BYTES;
+    WsCarve sm = ws_carve<NB>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nkt = (p.kdim + BK - 1) / BK;
+    if (tid == 0) {
+        for (int s = 0; s < WS_STAGES; s++) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], WS_CONSUMER_WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp < WS_PRODUCER_WARPS) {
+        reg_dealloc_producer();
+        if (tid == 0) {
+            prefetch_tmap(&metmap);
+            prefetch_tmap(&umap);
+            uint32_t g = 0;
+            int w = atomicAdd(p.counter, 1);
+            while (w < p.nitems) {
+                const int w_next = atomicAdd(p.counter, 1);
+                const int tm = w % p.ntm, tn = w / p.ntm;  // q tiles fastest: CTAs in flight share the U tile
+                for (int kt = 0; kt < nkt; kt++, g++) {
+                    const int s = g % WS_STAGES;
+                    mbar_wait(&sm.empty[s], ((g / WS_STAGES) & 1) ^ 1);
+                    if (kt == 0) sm.meta[s] = w;
+                    mbar_arrive_expect_tx(&sm.full[s], WS_A_STAGE + B_STAGE);
+                    tma_load_2d(sm.As + s * WS_A_STAGE, &metmap, kt * BK, tm * BM, &sm.full[s]);
+                    tma_load_2d(sm.Bs + s * B_STAGE, &umap, kt * BK, tn * BN, &sm.full[s]);
+                }
+                w = w_next;
+            }
+            const int s = g % WS_STAGES;
+            mbar_wait(&sm.empty[s], ((g / WS_STAGES) & 1) ^ 1);
+            sm.meta[s] = -1;
+            mbar_arrive(&sm.full[s]);
+        }
+        return;
+    }
+
+    reg_alloc_consumer();
+    const int cw = warp - WS_PRODUCER_WARPS;
+    const int wm = cw & 3, wn = cw >> 2, gq = lane >> 2, t = lane & 3;
+    int off[4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) off[ks] = (((ks + 4 * (t >> 1)) ^ gq) << 4) + ((t & 1) << 3);
+    const int a_row0 = (wm * 8 + gq) * WS_ROW_BYTES;
+    const int b_row0 = (wn * 8 * NB + gq) * WS_ROW_BYTES;
+    uint32_t g = 0;
+    for (;;) {
+        int s = g % WS_STAGES;
+        mbar_wait(&sm.full[s], (g / WS_STAGES) & 1);
+        const int w = sm.meta[s];
+        if (w < 0) break;
+        const int tm = w % p.ntm, tn = w / p.ntm;
+        const int mbv = live_row_blocks(p.nq - tm * BM, wm);
+        const int nbv = max(0, min(NB, (p.ncols - (tn * BN + wn * 8 * NB) + 7) / 8));
+        double acc[4][NB][2];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < NB; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+        for (int kt = 0; kt < nkt; kt++, g++) {
+            if (kt > 0) {
+                s = g % WS_STAGES;
+                mbar_wait(&sm.full[s], (g / WS_STAGES) & 1);
+            }
+            mma_stage_any<NB>(sm.As + s * WS_A_STAGE + a_row0, sm.Bs + s * B_STAGE + b_row0, off, acc, mbv, nbv);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[s]);
+        }
+#pragma unroll
+        for (int nb = 0; nb < NB; nb++) {
+            const int j0 = tn * BN + wn * 8 * NB + nb * 8 + t * 2;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int j = j0 + e;
+                if (j < p.ncols) {
+                    double* dst = p.tensor + p.dst_off[j];
+                    const size_t ld = (size_t)p.dst_ld[j];
+#pragma unroll
+                    for (int mb = 0; mb < 4; mb++) {
+                        const int q = tm * BM + mb * 32 + wm * 8 + gq;
+                        if (q < p.nq) dst[(size_t)q * ld] = acc[mb][nb][e];
+                    }
+                }
+            }
+        }
+    }
+}
+
 // K[m][n] += sum_s ws[s][tile][r][c]  (fixed order); mirrored for off-diagonal tiles when symmetric.
 __global__ void kgemm_reduce_list_kernel(const double* __restrict__ ws, int nsplit, int ntiles,
                                          const int2* __restrict__ tiles, int symmetric, int nbf, double* __restrict__ K) {

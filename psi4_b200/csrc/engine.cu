@@ -22,6 +22,7 @@
 #include "aux_kernels.cuh"
 #include "dmma_gemm.cuh"
 #include "dmma_ws.cuh"
+#include "fit_kernels.cuh"
 #include "j_kernels.cuh"
 
 using namespace b2k;
@@ -84,6 +85,16 @@ struct Shard {
     int* d_counter = nullptr;  // work-queue head of the persistent kernels
     int2 *d_tiles_sym = nullptr, *d_tiles_full = nullptr;  // K-GEMM tile lists, largest live area first
     int ntiles_sym = 0, ntiles_full = 0;
+    // on-device fitting (f2): mirror ranks, this shard's metric rows, staging
+    int* d_mpos = nullptr;
+    double* d_metric = nullptr;  // [nq][apitch]
+    bool have_metric = false;
+    double *fit_raw = nullptr, *fit_t = nullptr;
+    size_t fit_raw_cap = 0, fit_t_cap = 0;
+    size_t* d_fit_dst_off = nullptr;
+    size_t* d_fit_src_off = nullptr;
+    int *d_fit_dst_ld = nullptr, *d_fit_mi = nullptr, *d_fit_j0 = nullptr, *d_fit_m = nullptr;
+    size_t fit_cols_cap = 0, fit_nm_cap = 0;
     size_t tensor_doubles = 0;
     size_t* d_row_off = nullptr;
     int *d_ldm = nullptr, *d_sp = nullptr, *d_ign = nullptr, *d_cols = nullptr;
@@ -109,6 +120,9 @@ struct b200jk {
     bool uploaded[3] = {false, false, false};
     std::vector<size_t> small_skips, big_skips, row_off_unit;  // row_off_unit: sum of ldm up to m (per q row)
     std::vector<int> sp, ign, ldm, cols;
+    std::vector<int> mpos;                 // rank of m among the kept partners of n = cols[m][k] (mirror destination)
+    std::vector<size_t> symm_big_skips;    // dfhelper.cc:413-416: offsets of the symmetric-packed (n >= m) blocks
+    double ms_fit_gemm = 0, fit_flops = 0; // last b200jk_fit_rows: device time and flops of the metric contraction
     std::vector<size_t> cols_off;
     int max_sp = 0;
     uint64_t work_budget = 0;
@@ -777,7 +791,8 @@ void free_shard(Shard& s) {
         if (s.tensor[w]) cudaFree(s.tensor[w]);
         if (s.d_amaps[w]) cudaFree(s.d_amaps[w]);
     }
-    void* ptrs[] = {s.d_counter, s.d_tiles_sym, s.d_tiles_full,
+    void* ptrs[] = {s.d_counter, s.d_tiles_sym, s.d_tiles_full, s.d_mpos, s.d_metric, s.fit_raw, s.fit_t,
+                    s.d_fit_dst_off, s.d_fit_src_off, s.d_fit_dst_ld, s.d_fit_mi, s.d_fit_j0, s.d_fit_m,
                     s.d_row_off, s.d_ldm, s.d_sp, s.d_ign, s.d_cols, s.d_cols_off, s.in, s.out,
                     s.Ctl,       s.Ctr,   s.dpart, s.T1,  s.T2,     s.ws};
     for (void* p : ptrs)
@@ -931,6 +946,18 @@ int b200jk_set_layout(b200jk_t* h, size_t nbf, size_t naux, const size_t* small_
         h->max_sp = std::max(h->max_sp, (int)cnt);
     }
     if (small_skips[nbf] != tot || big_skips[nbf] != run) return fail(h, B200JK_ERR_INVALID, "table totals inconsistent");
+    // mirror ranks (the mask must be symmetric: dfhelper.cc:1670-1672 reads f(onu,omu) whenever f(omu,onu) != 0)
+    h->mpos.assign(h->cols.size(), 0);
+    h->symm_big_skips.assign(nbf + 1, 0);
+    for (size_t m = 0; m < nbf; m++) {
+        for (int k = 0; k < h->sp[m]; k++) {
+            size_t n = (size_t)h->cols[h->cols_off[m] + k];
+            size_t f = fun_index[n * nbf + m];
+            if (!f) return fail(h, B200JK_ERR_INVALID, "pair mask is not symmetric at (%zu,%zu)", m, n);
+            h->mpos[h->cols_off[m] + k] = (int)f - 1;
+        }
+        h->symm_big_skips[m + 1] = h->symm_big_skips[m] + (size_t)(h->sp[m] - h->ign[m]) * naux;
+    }
 
     // Q shards: contiguous, near-equal.  rank mode: this process owns shard `rank` of `world`.
     int nshard_total = h->rank_mode ? h->world : (int)h->sh.size();
@@ -951,6 +978,7 @@ int b200jk_set_layout(b200jk_t* h, size_t nbf, size_t naux, const size_t* small_
         if ((rc = upload_vec(h, &s.d_ign, h->ign))) return rc;
         if ((rc = upload_vec(h, &s.d_cols, h->cols))) return rc;
         if ((rc = upload_vec(h, &s.d_cols_off, h->cols_off))) return rc;
+        if ((rc = upload_vec(h, &s.d_mpos, h->mpos))) return rc;
         {
             // K-GEMM tile lists sorted by live area (rows x cols inside nbf), largest first
             const int n1d = ((int)nbf + BM - 1) / BM;
@@ -1415,3 +1443,5 @@ int b200jk_fp64_peak(b200jk_t* h, int kind, double seconds, double* out4) {
 }
 
 }  // extern "C"
+
+#include "fit_host.inl"

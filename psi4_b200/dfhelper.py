@@ -85,6 +85,20 @@ class DFHelper:
             out[a:b] = B[:, m, cols].ravel()
         return out
 
+    def pack_symm(self, dense_Amn: np.ndarray, m0: int = 0, m1: int | None = None) -> np.ndarray:
+        """(naux, nbf, nbf) -> the symmetric-packed buffer of compute_sparse_pQq_blocking_p_symm (dfhelper.cc:1338-1340)
+        for rows [m0, m1): block m is [naux][mi(m)] over the kept partners n >= m."""
+        m1 = self.nbf_ if m1 is None else m1
+        B = np.asarray(dense_Amn, dtype=np.float64)
+        base = int(self.symm_big_skips_[m0])
+        out = np.empty(int(self.symm_big_skips_[m1]) - base, dtype=np.float64)
+        for m in range(m0, m1):
+            cols = self.kept_columns(m)
+            cols = cols[cols >= m]
+            a, b = int(self.symm_big_skips_[m]) - base, int(self.symm_big_skips_[m + 1]) - base
+            out[a:b] = B[:, m, cols].ravel()
+        return out
+
     def unpack(self, packed: np.ndarray) -> np.ndarray:
         out = np.zeros((self.naux_, self.nbf_, self.nbf_))
         for m in range(self.nbf_):

@@ -141,7 +141,7 @@ class MemDFJK(JK):
     """
 
     def __init__(self, dfh: DFHelper, Ppq=None, m1Ppq=None, wPpq=None, *, ngpu: int = 1, devices=None,
-                 rank=None, world=None, device=None, nccl_id=None, synthetic=None):
+                 rank=None, world=None, device=None, nccl_id=None, synthetic=None, unfitted=None):
         super().__init__(dfh.nbf_)
         if not dfh.sparsity_prepared_:
             raise PsiException("MemDFJK: DFHelper sparsity not prepared")
@@ -149,6 +149,7 @@ class MemDFJK(JK):
         self.condition_ = 1.0e-12  # jk.h:1142
         self._Ppq, self._m1Ppq, self._wPpq = Ppq, m1Ppq, wPpq
         self._synthetic = synthetic  # (seed, amp) -> device-side fill, bench / large tests only
+        self._unfitted = unfitted    # (symmetric-packed unfitted (A|mn), metric power, rows per block) -> fit on device
         self._engine_args = dict(ngpu=ngpu, devices=devices, rank=rank, world=world, device=device, nccl_id=nccl_id)
         self.engine: _lib.Engine | None = None
 
@@ -178,6 +179,16 @@ class MemDFJK(JK):
         if self._synthetic is not None:
             seed, amp = self._synthetic
             self.engine.fill_synthetic(_lib.TENSOR_PPQ, seed, amp)
+        elif self._unfitted is not None:
+            # on-device fitting: the p-blocked loop of prepare_AO_core (dfhelper.cc:566-585) with the metric
+            # contraction + mirror copy (contract_metric_AO_core_symm, :1653-1678) done by the engine
+            sym, metric, block = self._unfitted
+            self.engine.set_metric(metric)
+            for m0 in range(0, d.nbf_, block):
+                m1 = min(d.nbf_, m0 + block)
+                self.engine.fit_rows(_lib.TENSOR_PPQ, m0, m1,
+                                     sym[int(d.symm_big_skips_[m0]):int(d.symm_big_skips_[m1])])
+            self._unfitted = None
         else:
             if self._Ppq is None:
                 raise PsiException("MemDFJK: no Ppq tensor supplied")

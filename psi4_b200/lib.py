@@ -66,6 +66,9 @@ SIGNATURES = {
     "b200jk_dev_free": (ct.c_int, [ct.c_void_p, ct.c_void_p]),
     "b200jk_dev_copy": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_size_t, ct.c_int]),
     "b200jk_fp64_peak": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_double, _dp]),
+    "b200jk_set_metric": (ct.c_int, [ct.c_void_p, _dp]),
+    "b200jk_fit_rows": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_size_t, ct.c_size_t, _dp]),
+    "b200jk_fit_stats": (ct.c_int, [ct.c_void_p, _dp, _dp]),
 }
 
 
@@ -156,6 +159,26 @@ class Engine:
         if p.size != need:
             raise B200JKError(1, f"row block has {p.size} doubles, layout says {need}")
         self._check(self.L.b200jk_upload_rows(self.h, which, m0, m1, _d(p)))
+
+    def set_metric(self, metric):
+        """naux x naux metric power for fit_rows (None: no contraction)."""
+        if metric is None:
+            self._check(self.L.b200jk_set_metric(self.h, None))
+            return
+        m = np.ascontiguousarray(metric, dtype=np.float64)
+        assert m.shape == (self.naux, self.naux)
+        self._check(self.L.b200jk_set_metric(self.h, _d(m)))
+
+    def fit_rows(self, which, m0, m1, sym_rows):
+        """Unfitted symmetric-packed rows [m0, m1) -> fitted, mirrored rows of tensor `which` (on the device)."""
+        p = np.ascontiguousarray(sym_rows, dtype=np.float64)
+        self._check(self.L.b200jk_fit_rows(self.h, which, m0, m1, _d(p)))
+
+    def fit_stats(self) -> dict:
+        ms, fl = ct.c_double(), ct.c_double()
+        self._check(self.L.b200jk_fit_stats(self.h, ct.byref(ms), ct.byref(fl)))
+        return {"ms_gemm": ms.value, "flops": fl.value,
+                "tflops": fl.value / (ms.value * 1e-3) / 1e12 if ms.value else 0.0}
 
     def fill_synthetic(self, which, seed, amp):
         a = np.ascontiguousarray(amp, dtype=np.float64)

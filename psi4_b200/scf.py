@@ -40,7 +40,7 @@ class DFTensors:
     """Host part of DFHelper::initialize for the in-core STORE method (dfhelper.cc:149-215, :514-588)."""
 
     def __init__(self, mol: Molecule, primary: BasisSet, aux: BasisSet, cutoff: float = 1e-12, condition: float = 1e-10,
-                 do_wK: bool = False):
+                 do_wK: bool = False, fit_on_device: bool = False):
         if do_wK:
             raise NotImplementedError("range-separated (erf-attenuated) integrals are not in the host front end yet")
         mints = MintsHelper(mol, primary)
@@ -51,17 +51,27 @@ class DFTensors:
         metric = mints.metric(aux)                                                 # prepare_metric :1462-1476
         self.Jm12 = matrix_power(metric, -0.5, condition)                          # compute_metric :1491-1517
         Amn = mints.three_center(aux)                                              # :1284-1347
-        # contract_metric_AO_core_symm :1653-1678  (B = J^-1/2 (A|mn)), then pack to pQq
-        B = np.tensordot(self.Jm12, Amn, axes=([1], [0]))
-        self.dense = B
-        self.Ppq = self.dfh.pack(B)
+        self.Ppq = self.dense = self.unfitted_sym = None
+        if fit_on_device:
+            # hand the unfitted n >= m half to the engine (b200jk_fit_rows); metric contraction + mirror run on the GPU
+            self.unfitted_sym = self.dfh.pack_symm(Amn)
+        else:
+            # contract_metric_AO_core_symm :1653-1678  (B = J^-1/2 (A|mn)) on the host, then pack to pQq
+            B = np.tensordot(self.Jm12, Amn, axes=([1], [0]))
+            self.dense = B
+            self.Ppq = self.dfh.pack(B)
 
 
 def build_jk(mol: Molecule, primary: BasisSet, aux: BasisSet, *, cutoff: float = 1e-12, condition: float = 1e-10,
-             ngpu: int = 1, jk_factory=None):
-    """JK::build_JK analogue.  jk_factory(dfh, Ppq) may construct another JK implementation (tests)."""
-    t = DFTensors(mol, primary, aux, cutoff, condition)
-    jk = (jk_factory or (lambda dfh, Ppq: MemDFJK(dfh, Ppq, ngpu=ngpu)))(t.dfh, t.Ppq)
+             ngpu: int = 1, jk_factory=None, fit_on_device: bool = False, fit_block: int = 64):
+    """JK::build_JK analogue.  jk_factory(dfh, Ppq) may construct another JK implementation (tests).
+    fit_on_device: the engine contracts the metric itself (b200jk_set_metric / b200jk_fit_rows), fed in blocks of
+    fit_block basis functions like the p-blocked loop of prepare_AO_core."""
+    t = DFTensors(mol, primary, aux, cutoff, condition, fit_on_device=fit_on_device)
+    if fit_on_device:
+        jk = MemDFJK(t.dfh, ngpu=ngpu, unfitted=(t.unfitted_sym, t.Jm12, fit_block))
+    else:
+        jk = (jk_factory or (lambda dfh, Ppq: MemDFJK(dfh, Ppq, ngpu=ngpu)))(t.dfh, t.Ppq)
     jk.set_cutoff(cutoff)
     if hasattr(jk, "set_condition"):
         jk.set_condition(condition)
