@@ -213,11 +213,21 @@ struct HalfWsParams {
     int nitems;
     int* counter;               // work queue head (zeroed before launch)
     double* T;                  // [nbf][qc][op]
+    // Fused first J sweep (dfhelper.cc:3193 / :3258): the last orbital tile carries one extra B-operand row, the
+    // density row D'[m, n_k], so its accumulator column is d_part[m][q] = sum_k B_m[q,k] D'[m,n_k] -- the tensor
+    // tile is already in shared memory, the separate HBM sweep of j_dq_kernel disappears.
+    int fuse;                   // 0 / 1
+    int rd;                     // row of the density inside the last i-tile (= o - (nit-1)*iw < 16*NB)
+    const double* Dm;           // [nbf][ldd]  D (general) or D symmetrised from its upper triangle (lr_symmetric)
+    int ldd;
+    double* dpart;              // [nbf][dstride]
+    int dstride;
 };
 
 template <int NB>
 __global__ void __launch_bounds__(WS_THREADS, 1)
-    half_ws_kernel(const __grid_constant__ CUtensorMap ctmap, HalfWsParams p) {
+    half_ws_kernel(const __grid_constant__ CUtensorMap ctmap, const __grid_constant__ CUtensorMap ctmap_last,
+                   const __grid_constant__ CUtensorMap dmap, HalfWsParams p) {
     extern __shared__ uint8_t smem_raw[];
     constexpr int BN = 16 * NB;
     constexpr int B_STAGE = BN * WS_ROW_BYTES;
@@ -254,6 +264,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
             const bool dense = (K == p.nbf);
             const int i0 = it * p.iw;
             const CUtensorMap* amap = p.amaps + m;
+            const bool fused = p.fuse && it == p.nit - 1;  // this tile also carries the density row (row p.rd)
             if (dense) {
                 // both operands by TMA; one thread drives the whole stage
                 if (tid == 0) {
@@ -262,9 +273,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
                         const int s = gg % WS_STAGES;
                         mbar_wait(&sm.empty[s], ((gg / WS_STAGES) & 1) ^ 1);
                         if (kt == 0) sm.meta[s] = w;
-                        mbar_arrive_expect_tx(&sm.full[s], WS_A_STAGE + B_STAGE);
-                        tma_load_2d(sm.As + s * WS_A_STAGE, amap, kt * BK, p.qbeg + qt * BM, &sm.full[s]);
-                        tma_load_2d(sm.Bs + s * B_STAGE, &ctmap, kt * BK, i0, &sm.full[s]);
+                        if (!fused) {
+                            mbar_arrive_expect_tx(&sm.full[s], WS_A_STAGE + B_STAGE);
+                            tma_load_2d(sm.As + s * WS_A_STAGE, amap, kt * BK, p.qbeg + qt * BM, &sm.full[s]);
+                            tma_load_2d(sm.Bs + s * B_STAGE, &ctmap, kt * BK, i0, &sm.full[s]);
+                        } else {
+                            // C^T box stops at row rd (its own map) so that it cannot race with the density row;
+                            // rows above rd keep stale finite-or-not data that only feeds discarded columns
+                            mbar_arrive_expect_tx(&sm.full[s], WS_A_STAGE + (p.rd + 1) * WS_ROW_BYTES);
+                            tma_load_2d(sm.As + s * WS_A_STAGE, amap, kt * BK, p.qbeg + qt * BM, &sm.full[s]);
+                            tma_load_2d(sm.Bs + s * B_STAGE, &ctmap_last, kt * BK, i0, &sm.full[s]);
+                            tma_load_2d(sm.Bs + s * B_STAGE + p.rd * WS_ROW_BYTES, &dmap, kt * BK, m, &sm.full[s]);
+                        }
                         mbar_arrive_n(&sm.full[s], WS_PRODUCER_THREADS);
                     }
                 }
@@ -272,6 +292,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
             } else {
                 const int irows = min(p.o, i0 + BN) - i0;  // valid C^T rows of this tile
                 const int* cols = p.cols + p.cols_off[m];
+                const double* drow = p.Dm + (size_t)m * p.ldd;
                 int col_next = (kk < K) ? __ldg(cols + kk) : -1;
                 for (int kt = 0; kt < nkt; kt++, g++) {
                     const int s = g % WS_STAGES;
@@ -288,8 +309,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
                     uint8_t* bs = sm.Bs + s * B_STAGE;
 #pragma unroll 4
                     for (int r = tid >> 4; r < BN; r += WS_PRODUCER_THREADS / 16) {
-                        int bytes = (col >= 0 && r < irows) ? 8 : 0;
-                        const double* src = bytes ? p.Ct + (size_t)(i0 + r) * p.ldc + col : p.Ct;
+                        const bool drow_here = fused && r == p.rd;
+                        int bytes = (col >= 0 && (r < irows || drow_here)) ? 8 : 0;
+                        const double* src = !bytes ? p.Ct : (drow_here ? drow + col : p.Ct + (size_t)(i0 + r) * p.ldc + col);
                         double* dst =
                             reinterpret_cast<double*>(bs + r * WS_ROW_BYTES + ((chunk ^ (r & 7)) << 4) + (half << 3));
                         cp_async8(dst, src, bytes);
@@ -333,7 +355,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         const int K = p.sp[m];
         const int nkt = (K + BK - 1) / BK;
         const int q0 = qt * BM, i0 = it * p.iw;
-        const int icols = min(p.iw, p.o - i0);
+        const bool fused = p.fuse && it == p.nit - 1;
+        const int icols = min(p.iw, p.o - i0) + (fused ? 1 : 0);  // + the density column
         const int mbv = live_row_blocks(p.qc - q0, wm);
         const int nbv = max(0, min(NB, (icols - wn * 8 * NB + 7) / 8));
         double acc[4][NB][2];
@@ -363,8 +386,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
                 for (int nb = 0; nb < NB; nb++) {
                     int ic = wn * 8 * NB + nb * 8 + t * 2;
                     int i = i0 + ic;
-                    if (ic < p.iw && i < p.op)
-                        *reinterpret_cast<double2*>(Tm + (size_t)q * p.op + i) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+                    double v0 = acc[mb][nb][0], v1 = acc[mb][nb][1];
+                    if (fused && (ic == p.rd || ic + 1 == p.rd)) {
+                        // density column: goes to d_part, and is NOT part of T (it may sit on T's zero pad column)
+                        p.dpart[(size_t)m * p.dstride + p.qbeg + q] = (ic == p.rd) ? v0 : v1;
+                        if (ic == p.rd) v0 = 0.0; else v1 = 0.0;
+                    }
+                    if (ic < p.iw && i < p.op) *reinterpret_cast<double2*>(Tm + (size_t)q * p.op + i) = make_double2(v0, v1);
                 }
             }
         }

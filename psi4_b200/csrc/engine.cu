@@ -89,6 +89,9 @@ struct Shard {
     int* d_mpos = nullptr;
     double* d_metric = nullptr;  // [nq][apitch]
     bool have_metric = false;
+    double* Dm = nullptr;        // [nmat][nbf][ldd] density operands of the fused first J sweep
+    size_t dm_cap = 0;
+    std::vector<char> fused;     // per density of the current build: first J sweep done inside the half transform
     double *fit_raw = nullptr, *fit_t = nullptr;
     size_t fit_raw_cap = 0, fit_t_cap = 0;
     size_t* d_fit_dst_off = nullptr;
@@ -277,7 +280,8 @@ bool use_legacy() {
 }
 
 template <int NB>
-int launch_half_ws(b200jk* h, Shard& s, const CUtensorMap& ctmap, const HalfWsParams& p) {
+int launch_half_ws(b200jk* h, Shard& s, const CUtensorMap& ctmap, const CUtensorMap& ctmap_last, const CUtensorMap& dmap,
+                   const HalfWsParams& p) {
     static bool attr_set[64] = {false};
     constexpr size_t smem = ws_smem_bytes<NB>();
     if (!attr_set[s.dev]) {
@@ -286,21 +290,60 @@ int launch_half_ws(b200jk* h, Shard& s, const CUtensorMap& ctmap, const HalfWsPa
     }
     int grid = std::min(p.nitems, s.nsm);
     CK(cudaMemsetAsync(s.d_counter, 0, sizeof(int), s.stream));
-    half_ws_kernel<NB><<<grid, WS_THREADS, smem, s.stream>>>(ctmap, p);
+    half_ws_kernel<NB><<<grid, WS_THREADS, smem, s.stream>>>(ctmap, ctmap_last, dmap, p);
     s.launches++;
     CK(cudaGetLastError());
     return 0;
 }
 
-int run_half_ws(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o, int op, int qbeg, int qc, double* T) {
-    int nit = (o + 127) / 128;
-    // orbital columns per tile: whole 8-column DMMA blocks, so a ragged nocc pads only the last block of the last tile
-    int iw = std::min(128, round_up((op + nit - 1) / nit, 8));
-    int NB = (iw + 15) / 16;
-    CUtensorMap ctmap;
+// Density operand of the fused first J sweep (see HalfWsParams): nullptr = plain half transform.
+struct FuseJ {
+    const double* Dm;
+    int ldd;
+    double* dpart;
+    int dstride;
+};
+
+// orbital tiling of the half transform: nit tiles of iw columns (whole 8-column DMMA blocks), NB blocks per warp pair
+void half_tiling(int o, int op, int* nit, int* iw, int* NB) {
+    *nit = (o + 127) / 128;
+    *iw = std::min(128, round_up((op + *nit - 1) / *nit, 8));
+    *NB = (*iw + 15) / 16;
+}
+// the density row needs a free B-operand row in the last orbital tile
+bool can_fuse_j(int o) {
+    static int off = -1;
+    if (off < 0) {
+        const char* e = getenv("B200JK_NO_JFUSE");
+        off = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (off || use_legacy() || o <= 0) return false;
+    int nit, iw, NB;
+    half_tiling(o, round_up(o, 2), &nit, &iw, &NB);
+    return o - (nit - 1) * iw < 16 * NB;
+}
+
+int run_half_ws(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o, int op, int qbeg, int qc, double* T,
+                const FuseJ* fj) {
+    int nit, iw, NB;
+    half_tiling(o, op, &nit, &iw, &NB);
+    CUtensorMap ctmap, ctmap_last, dmap;
     int rc = make_map(h, &ctmap, Ct, h->nbf, (uint64_t)o, (uint64_t)ldc * 8, (uint32_t)(16 * NB));
     if (rc) return rc;
+    ctmap_last = ctmap;
+    dmap = ctmap;
+    const int rd = o - (nit - 1) * iw;
+    if (fj) {
+        if ((rc = make_map(h, &ctmap_last, Ct, h->nbf, (uint64_t)o, (uint64_t)ldc * 8, (uint32_t)rd))) return rc;
+        if ((rc = make_map(h, &dmap, fj->Dm, h->nbf, h->nbf, (uint64_t)fj->ldd * 8, 1))) return rc;
+    }
     HalfWsParams p;
+    p.fuse = fj ? 1 : 0;
+    p.rd = rd;
+    p.Dm = fj ? fj->Dm : nullptr;
+    p.ldd = fj ? fj->ldd : 0;
+    p.dpart = fj ? fj->dpart : nullptr;
+    p.dstride = fj ? fj->dstride : 0;
     p.amaps = s.d_amaps[which];
     p.sp = s.d_sp;
     p.cols = s.d_cols;
@@ -319,14 +362,14 @@ int run_half_ws(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o
     p.counter = s.d_counter;
     p.T = T;
     switch (NB) {
-        case 1: return launch_half_ws<1>(h, s, ctmap, p);
-        case 2: return launch_half_ws<2>(h, s, ctmap, p);
-        case 3: return launch_half_ws<3>(h, s, ctmap, p);
-        case 4: return launch_half_ws<4>(h, s, ctmap, p);
-        case 5: return launch_half_ws<5>(h, s, ctmap, p);
-        case 6: return launch_half_ws<6>(h, s, ctmap, p);
-        case 7: return launch_half_ws<7>(h, s, ctmap, p);
-        default: return launch_half_ws<8>(h, s, ctmap, p);
+        case 1: return launch_half_ws<1>(h, s, ctmap, ctmap_last, dmap, p);
+        case 2: return launch_half_ws<2>(h, s, ctmap, ctmap_last, dmap, p);
+        case 3: return launch_half_ws<3>(h, s, ctmap, ctmap_last, dmap, p);
+        case 4: return launch_half_ws<4>(h, s, ctmap, ctmap_last, dmap, p);
+        case 5: return launch_half_ws<5>(h, s, ctmap, ctmap_last, dmap, p);
+        case 6: return launch_half_ws<6>(h, s, ctmap, ctmap_last, dmap, p);
+        case 7: return launch_half_ws<7>(h, s, ctmap, ctmap_last, dmap, p);
+        default: return launch_half_ws<8>(h, s, ctmap, ctmap_last, dmap, p);
     }
 }
 
@@ -389,8 +432,9 @@ int launch_half(b200jk* h, Shard& s, const HalfParams& p, dim3 grid) {
 }
 
 // T[m][q][i] for q in the chunk [qbeg, qbeg+qc): one launch over (i-tiles, q-tiles, m).
-int run_half(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o, int op, int qbeg, int qc, double* T) {
-    if (!use_legacy()) return run_half_ws(h, s, which, Ct, ldc, o, op, qbeg, qc, T);
+int run_half(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o, int op, int qbeg, int qc, double* T,
+             const FuseJ* fj = nullptr) {
+    if (!use_legacy()) return run_half_ws(h, s, which, Ct, ldc, o, op, qbeg, qc, T, fj);
     const double* tensor = s.tensor[which];
     int nit = (o + 127) / 128;
     int iw = round_up((op + nit - 1) / nit, 2);
@@ -459,7 +503,8 @@ int run_kgemm(b200jk* h, Shard& s, const double* T1, const double* T2, int kdim,
     return 0;
 }
 
-int run_j(b200jk* h, Shard& s, const double* D, bool symmetric, double* Jout) {
+// J sweeps of one density.  first_sweep_done: d_part was already produced by the fused half transform.
+int run_j(b200jk* h, Shard& s, const double* D, bool symmetric, double* Jout, double* dpart, bool first_sweep_done) {
     JParams p;
     p.tensor = s.tensor[B200JK_TENSOR_PPQ];
     p.row_off = s.d_row_off;
@@ -472,7 +517,7 @@ int run_j(b200jk* h, Shard& s, const double* D, bool symmetric, double* Jout) {
     p.nq = s.nq;
     p.symmetric = symmetric ? 1 : 0;
     p.D = D;
-    p.dpart = s.dpart;
+    p.dpart = dpart;
     p.d = s.dvec;
     p.J = Jout;
     static bool attr_set[64] = {false};
@@ -486,10 +531,12 @@ int run_j(b200jk* h, Shard& s, const double* D, bool symmetric, double* Jout) {
     if (sm1 > 200 * 1024 || sm2 > 200 * 1024)
         return fail(h, B200JK_ERR_INVALID, "J kernels: nbf %d / shard naux %d exceed the shared-memory staging limit",
                     h->max_sp, s.nq);
-    j_dq_kernel<<<dim3((s.nq + J1_ROWS - 1) / J1_ROWS, (unsigned)h->nbf), J_THREADS, sm1, s.stream>>>(p);
-    s.launches++;
-    CK(cudaGetLastError());
-    j_dq_reduce_kernel<<<(s.nq + 127) / 128, 128, 0, s.stream>>>(s.dpart, p.nbf, s.nq, s.dvec);
+    if (!first_sweep_done) {
+        j_dq_kernel<<<dim3((s.nq + J1_ROWS - 1) / J1_ROWS, (unsigned)h->nbf), J_THREADS, sm1, s.stream>>>(p);
+        s.launches++;
+        CK(cudaGetLastError());
+    }
+    j_dq_reduce_kernel<<<(s.nq + 127) / 128, 128, 0, s.stream>>>(dpart, p.nbf, s.nq, s.dvec);
     s.launches++;
     CK(cudaGetLastError());
     j_mn_kernel<<<dim3((h->max_sp + 127) / 128, (unsigned)h->nbf), J_THREADS, sm2, s.stream>>>(p);
@@ -522,9 +569,12 @@ int ensure_work(b200jk* h, Shard& s, const Task& t, int* qc_out) {
     size_t N = h->nbf;
     if ((rc = grow(h, &s.out, &s.out_cap, (size_t)t.nmat * t.nprod * t.n2))) return rc;
     if (t.do_J) {
-        if ((rc = grow(h, &s.dpart, &s.dpart_cap, N * (size_t)s.nq + (size_t)s.nq))) return rc;
-        s.dvec = s.dpart + N * (size_t)s.nq;
+        // one d_part per density: the fused half transforms of all densities run before the J sweeps
+        if ((rc = grow(h, &s.dpart, &s.dpart_cap, (size_t)t.nmat * N * (size_t)s.nq + (size_t)s.nq))) return rc;
+        s.dvec = s.dpart + (size_t)t.nmat * N * (size_t)s.nq;
+        if (t.do_K && (rc = grow(h, &s.Dm, &s.dm_cap, (size_t)t.nmat * N * (size_t)round_up((int)N, 2)))) return rc;
     }
+    s.fused.assign(t.nmat, 0);
     *qc_out = 0;
     if ((t.do_K || t.do_wK) && t.max_o > 0) {
         int op = round_up(t.max_o, 2);
@@ -602,12 +652,16 @@ int run_device_J(b200jk* h, Shard& s, const Task& t, const double* const* dD) {
     int rc;
     PhaseScope ps(s, 0);
     for (int i = 0; i < t.nmat; i++)
-        if ((rc = run_j(h, s, dD[i], t.lr, s.out + ol.offJ + i * t.n2))) return rc;
+        if ((rc = run_j(h, s, dD[i], t.lr, s.out + ol.offJ + i * t.n2, s.dpart + (size_t)i * h->nbf * (size_t)s.nq,
+                        s.fused[i] != 0)))
+            return rc;
     return 0;
 }
 
-// The K and wK builds of one shard (K3, K4 per density and Q chunk).
-int run_device_K(b200jk* h, Shard& s, const Task& t, const double* const* dCl, const double* const* dCr, int qc) {
+// The K and wK builds of one shard (K3, K4 per density and Q chunk).  When J is tasked too (dD != nullptr) the first
+// half transform of each density also produces d_part, the first J sweep (see HalfWsParams).
+int run_device_K(b200jk* h, Shard& s, const Task& t, const double* const* dCl, const double* const* dCr,
+                 const double* const* dD, int qc) {
     if (!t.do_K && !t.do_wK) return 0;
     CK(cudaSetDevice(s.dev));
     const size_t N = h->nbf, n2 = t.n2;
@@ -633,11 +687,26 @@ int run_device_K(b200jk* h, Shard& s, const Task& t, const double* const* dCl, c
                 if (!one_T && (rc = run_transpose(h, s, t.lr ? dCl[i] : dCr[i], o, s.Ctr, ldc, op))) return rc;
             }
             double* Kout = (wk ? outW : outK) + i * n2;
+            FuseJ fj_store, *fj = nullptr;
+            if (!wk && t.do_J && dD && dD[i] && can_fuse_j(o)) {
+                const int ldd = round_up((int)N, 2);
+                fj_store.Dm = s.Dm + (size_t)i * N * ldd;
+                fj_store.ldd = ldd;
+                fj_store.dpart = s.dpart + (size_t)i * N * (size_t)s.nq;
+                fj_store.dstride = s.nq;
+                fj = &fj_store;
+                PhaseScope ps(s, 0);
+                j_prep_dm_kernel<<<dim3((ldd + 127) / 128, (unsigned)N), 128, 0, s.stream>>>(dD[i], (int)N, ldd, t.lr ? 1 : 0,
+                                                                                          s.Dm + (size_t)i * N * ldd);
+                s.launches++;
+                CK(cudaGetLastError());
+                s.fused[i] = 1;
+            }
             for (int qb = 0; qb < s.nq; qb += qc) {
                 int nqc = std::min(qc, s.nq - qb);
                 {
                     PhaseScope ps(s, 1);
-                    if ((rc = run_half(h, s, tenL, s.Ctl, ldc, o, op, qb, nqc, s.T1))) return rc;
+                    if ((rc = run_half(h, s, tenL, s.Ctl, ldc, o, op, qb, nqc, s.T1, fj))) return rc;
                     if (!one_T && (rc = run_half(h, s, tenR, s.Ctr, ldc, o, op, qb, nqc, s.T2))) return rc;
                 }
                 {
@@ -666,7 +735,9 @@ void account_work(b200jk* h, const Task& t) {
     for (auto& s : h->sh) Aloc += s.nq;
     st.j_bytes = st.half_flops = st.half_bytes = st.kgemm_flops = 0;
     for (int i = 0; i < t.nmat; i++) {
-        if (t.do_J) st.j_bytes += 2.0 * 8.0 * Aloc * (t.lr ? Ptri : P);
+        // a fused first sweep rides on the half transform's read of the tensor: only the second sweep is J traffic
+        const bool fused = !h->sh.empty() && (int)h->sh[0].fused.size() > i && h->sh[0].fused[i];
+        if (t.do_J) st.j_bytes += (fused ? 1.0 : 2.0) * 8.0 * Aloc * (t.lr ? Ptri : P);
         double o = t.nocc[i];
         if (o == 0) continue;
         if (t.do_K) {
@@ -791,7 +862,7 @@ void free_shard(Shard& s) {
         if (s.tensor[w]) cudaFree(s.tensor[w]);
         if (s.d_amaps[w]) cudaFree(s.d_amaps[w]);
     }
-    void* ptrs[] = {s.d_counter, s.d_tiles_sym, s.d_tiles_full, s.d_mpos, s.d_metric, s.fit_raw, s.fit_t,
+    void* ptrs[] = {s.d_counter, s.d_tiles_sym, s.d_tiles_full, s.d_mpos, s.d_metric, s.fit_raw, s.fit_t, s.Dm,
                     s.d_fit_dst_off, s.d_fit_src_off, s.d_fit_dst_ld, s.d_fit_mi, s.d_fit_j0, s.d_fit_m,
                     s.d_row_off, s.d_ldm, s.d_sp, s.d_ign, s.d_cols, s.d_cols_off, s.in, s.out,
                     s.Ctl,       s.Ctr,   s.dpart, s.T1,  s.T2,     s.ws};
@@ -1223,19 +1294,17 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
         }
     }
 
-    // K / wK kernels
+    // D goes up on the copy stream: under the K kernels normally, ahead of them when the first J sweep is fused
+    // into the half transform (the density row is then an operand of K3)
+    bool fuse_any = false;
+    if (do_J && do_K)
+        for (int i = 0; i < nmat; i++) fuse_any = fuse_any || (nocc[i] > 0 && can_fuse_j(nocc[i]));
     std::vector<cudaEvent_t> evK(nsh), evD(nsh);
     for (size_t si = 0; si < nsh; si++) {
-        Shard& s = h->sh[si];
-        if ((rc = run_device_K(h, s, t, dCl[si].data(), dCr[si].data(), qc[si]))) return rc;
-        CK(cudaSetDevice(s.dev));
-        evK[si] = get_event(s);
-        evD[si] = get_event(s);
-        CK(cudaEventRecord(evK[si], s.stream));
+        evK[si] = get_event(h->sh[si]);
+        evD[si] = get_event(h->sh[si]);
     }
-
-    // D goes up on the copy stream while K computes
-    if (host_ops && do_J) {
+    auto upload_D = [&]() -> int {
         for (int i = 0; i < nmat; i++) par_memcpy(h->pin_in + c_doubles + (size_t)i * n2, D[i], n2 * 8);
         for (size_t si = 0; si < nsh; si++) {
             Shard& s = h->sh[si];
@@ -1251,7 +1320,18 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
             CK(cudaEventRecord(evD[si], s.copy));
             CK(cudaStreamWaitEvent(s.stream, evD[si], 0));
         }
+        return 0;
+    };
+    if (host_ops && do_J && fuse_any && (rc = upload_D())) return rc;
+
+    // K / wK kernels
+    for (size_t si = 0; si < nsh; si++) {
+        Shard& s = h->sh[si];
+        if ((rc = run_device_K(h, s, t, dCl[si].data(), dCr[si].data(), do_J ? dD[si].data() : nullptr, qc[si]))) return rc;
+        CK(cudaSetDevice(s.dev));
+        CK(cudaEventRecord(evK[si], s.stream));
     }
+    if (host_ops && do_J && !fuse_any && (rc = upload_D())) return rc;
 
     // J sweeps
     for (size_t si = 0; si < nsh; si++)

@@ -104,6 +104,18 @@ __global__ void j_dq_reduce_kernel(const double* __restrict__ dpart, int nbf, in
     d[q] = (s0 + s1) + (s2 + s3);
 }
 
+// Density operand of the fused first sweep (half_ws_kernel): Dm[m][n] = D[m][n], or, for lr_symmetric builds,
+// D[min(m,n)][max(m,n)] -- the symmetric path reads only the upper triangle of D (dfhelper.cc:3185-3190: D_mm and
+// 2 D_mn for n > m over the n >= m half of a tensor that is symmetric in mn  ==  the full sum with this Dm).
+__global__ void j_prep_dm_kernel(const double* __restrict__ D, int nbf, int ldd, int symmetric, double* __restrict__ Dm) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    int m = blockIdx.y;
+    if (n >= ldd) return;
+    double v = 0.0;
+    if (n < nbf) v = (symmetric && n < m) ? D[(size_t)n * nbf + m] : D[(size_t)m * nbf + n];
+    Dm[(size_t)m * ldd + n] = v;
+}
+
 // K2.  grid = (ceil(max_sp/128), nbf).  CTA: row-block m, packed columns [kt*128, kt*128+128).
 // Warp w sums rows q = w, w+8, ...; lane owns columns 2*lane,+1 and 64+2*lane,+1.  Cross-warp
 // reduction in shared memory in fixed order, then the sparse->dense unpack writes J directly.
