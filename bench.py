@@ -237,6 +237,9 @@ def main():
     st_dev = eng.stats()
 
     # ---- end-to-end arm: host pointers through b200jk_compute ----
+    # D, J, K live in persistent caller matrices, as psi4's D_ao_/J_ao_/K_ao_ do (allocated once, jk.cc:355-446); the
+    # glue page-locks them once (b200jk_register_host).  C is a fresh pageable array every iteration and is staged.
+    eng.register_host(D[0])
     for _ in range(min(args.warmup, 2)):
         eng.compute(Cl, Crl, D, reuse_outputs=True)
     barrier()

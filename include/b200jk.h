@@ -122,6 +122,13 @@ int b200jk_compute(b200jk_t* h, int nmat, const double* const* Cl, const double*
                    const double* const* D, double* const* J, double* const* K, double* const* wK, int do_J,
                    int do_K, int do_wK);
 
+/* Optional: page-lock caller memory that persists across builds (psi4 allocates D_ao_/J_ao_/K_ao_ once in
+ * JK::allocate_JK / USO2AO, jk.cc:355-446) so b200jk_compute DMAs straight from/to it instead of staging through
+ * the engine's pinned buffers.  Any D/J/K/wK pointer inside a registered range is used in place; everything else
+ * is staged.  Unregister before freeing the memory (b200jk_destroy unregisters what is left). */
+int b200jk_register_host(b200jk_t* h, void* ptr, size_t bytes);
+int b200jk_unregister_host(b200jk_t* h, void* ptr);
+
 /* Same build with every operand already resident in this rank's HBM (device pointers); used by
  * the kernel-only timing of bench.py and by callers that keep C/D on the GPU.  Rank mode only
  * (one shard per handle).  Outputs hold the all-reduced result on every rank. */

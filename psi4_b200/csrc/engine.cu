@@ -134,7 +134,18 @@ struct b200jk {
     size_t pin_in_cap = 0, pin_out_cap = 0;
     std::string err;
     b200jk_stats stats;
+    std::vector<std::pair<const char*, size_t>> pinned;  // caller ranges registered with b200jk_register_host
 };
+
+namespace {
+// true if [p, p+bytes) lies inside a range the caller registered (page-locked): DMA can use it directly
+bool is_pinned(const b200jk* h, const void* p, size_t bytes) {
+    const char* c = (const char*)p;
+    for (auto& r : h->pinned)
+        if (c >= r.first && c + bytes <= r.first + r.second) return true;
+    return false;
+}
+}  // namespace
 
 namespace {
 
@@ -961,8 +972,31 @@ int b200jk_create_rank(b200jk_t** out, int device, int rank, int world, const vo
     return 0;
 }
 
+int b200jk_register_host(b200jk_t* h, void* ptr, size_t bytes) {
+    if (!h || !ptr || !bytes) return B200JK_ERR_INVALID;
+    if (h->sh.empty()) return fail(h, B200JK_ERR_NODEVICE, "handle has no device");
+    if (is_pinned(h, ptr, bytes)) return 0;
+    CK(cudaSetDevice(h->sh[0].dev));
+    CK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    h->pinned.push_back({(const char*)ptr, bytes});
+    return 0;
+}
+
+int b200jk_unregister_host(b200jk_t* h, void* ptr) {
+    if (!h || !ptr) return B200JK_ERR_INVALID;
+    for (size_t i = 0; i < h->pinned.size(); i++) {
+        if (h->pinned[i].first == (const char*)ptr) {
+            CK(cudaHostUnregister(ptr));
+            h->pinned.erase(h->pinned.begin() + i);
+            return 0;
+        }
+    }
+    return fail(h, B200JK_ERR_INVALID, "pointer was not registered");
+}
+
 void b200jk_destroy(b200jk_t* h) {
     if (!h) return;
+    for (auto& r : h->pinned) cudaHostUnregister((void*)r.first);
     for (auto& s : h->sh) free_shard(s);
     if (h->pin_in) cudaFreeHost(h->pin_in);
     if (h->pin_out) cudaFreeHost(h->pin_out);
@@ -1305,7 +1339,16 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
         evD[si] = get_event(h->sh[si]);
     }
     auto upload_D = [&]() -> int {
-        for (int i = 0; i < nmat; i++) par_memcpy(h->pin_in + c_doubles + (size_t)i * n2, D[i], n2 * 8);
+        // densities in caller memory registered with b200jk_register_host go up by DMA as they are; others are staged
+        std::vector<const double*> srcD(nmat);
+        for (int i = 0; i < nmat; i++) {
+            if (is_pinned(h, D[i], n2 * 8)) {
+                srcD[i] = D[i];
+            } else {
+                par_memcpy(h->pin_in + c_doubles + (size_t)i * n2, D[i], n2 * 8);
+                srcD[i] = h->pin_in + c_doubles + (size_t)i * n2;
+            }
+        }
         for (size_t si = 0; si < nsh; si++) {
             Shard& s = h->sh[si];
             CK(cudaSetDevice(s.dev));
@@ -1314,7 +1357,8 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
             ph.a = get_event(s);
             ph.b = get_event(s);
             CK(cudaEventRecord(ph.a, s.copy));
-            CK(cudaMemcpyAsync(s.in + c_doubles, h->pin_in + c_doubles, d_doubles * 8, cudaMemcpyHostToDevice, s.copy));
+            for (int i = 0; i < nmat; i++)
+                CK(cudaMemcpyAsync(s.in + c_doubles + (size_t)i * n2, srcD[i], n2 * 8, cudaMemcpyHostToDevice, s.copy));
             CK(cudaEventRecord(ph.b, s.copy));
             s.phases.push_back(ph);
             CK(cudaEventRecord(evD[si], s.copy));
@@ -1354,7 +1398,14 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
             ph.a = get_event(s0);
             ph.b = get_event(s0);
             CK(cudaEventRecord(ph.a, s0.copy));
-            CK(cudaMemcpyAsync(h->pin_out + ol.offK, s0.out + ol.offK, ol.countKW * 8, cudaMemcpyDeviceToHost, s0.copy));
+            size_t off = ol.offK;
+            for (int pr = 1; pr < 3; pr++) {
+                if (!outs[pr]) continue;
+                for (int i = 0; i < nmat; i++, off += n2) {
+                    double* dst = is_pinned(h, outs[pr][i], n2 * 8) ? outs[pr][i] : h->pin_out + off;  // registered: DMA home
+                    CK(cudaMemcpyAsync(dst, s0.out + off, n2 * 8, cudaMemcpyDeviceToHost, s0.copy));
+                }
+            }
             CK(cudaEventRecord(ph.b, s0.copy));
             s0.phases.push_back(ph);
         }
@@ -1364,7 +1415,11 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
         CK(cudaSetDevice(s0.dev));
         if (ol.countJ) {
             PhaseScope ps(s0, 5);
-            CK(cudaMemcpyAsync(h->pin_out + ol.offJ, s0.out + ol.offJ, ol.countJ * 8, cudaMemcpyDeviceToHost, s0.stream));
+            for (int i = 0; i < nmat; i++) {
+                size_t off = ol.offJ + (size_t)i * n2;
+                double* dst = is_pinned(h, J[i], n2 * 8) ? J[i] : h->pin_out + off;
+                CK(cudaMemcpyAsync(dst, s0.out + off, n2 * 8, cudaMemcpyDeviceToHost, s0.stream));
+            }
         }
         // every shard's compute stream also waits for its copy stream so `total` covers both
         for (size_t si = 0; si < nsh; si++) {
@@ -1397,7 +1452,8 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
         size_t off = ol.offK;
         for (int pr = 1; pr < 3; pr++) {
             if (!outs[pr]) continue;
-            for (int i = 0; i < nmat; i++, off += n2) par_memcpy(outs[pr][i], h->pin_out + off, n2 * 8);
+            for (int i = 0; i < nmat; i++, off += n2)
+                if (!is_pinned(h, outs[pr][i], n2 * 8)) par_memcpy(outs[pr][i], h->pin_out + off, n2 * 8);
         }
     }
     for (auto& s : h->sh) {
@@ -1406,7 +1462,8 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
         CK(cudaStreamSynchronize(s.copy));
     }
     if (host_ops && do_J)
-        for (int i = 0; i < nmat; i++) par_memcpy(J[i], h->pin_out + ol.offJ + (size_t)i * n2, n2 * 8);
+        for (int i = 0; i < nmat; i++)
+            if (!is_pinned(h, J[i], n2 * 8)) par_memcpy(J[i], h->pin_out + ol.offJ + (size_t)i * n2, n2 * 8);
     account_work(h, t);
     collect_stats(h);
     h->stats.hbm_work_bytes = 0;

@@ -66,6 +66,8 @@ SIGNATURES = {
     "b200jk_dev_free": (ct.c_int, [ct.c_void_p, ct.c_void_p]),
     "b200jk_dev_copy": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_size_t, ct.c_int]),
     "b200jk_fp64_peak": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_double, _dp]),
+    "b200jk_register_host": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_size_t]),
+    "b200jk_unregister_host": (ct.c_int, [ct.c_void_p, ct.c_void_p]),
     "b200jk_set_metric": (ct.c_int, [ct.c_void_p, _dp]),
     "b200jk_fit_rows": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_size_t, ct.c_size_t, _dp]),
     "b200jk_fit_stats": (ct.c_int, [ct.c_void_p, _dp, _dp]),
@@ -199,7 +201,18 @@ class Engine:
         key = (tag, nmat, n)
         if key not in cache:
             cache[key] = [np.zeros((n, n)) for _ in range(nmat)]  # zeros: pages touched once, here
+            for a in cache[key]:
+                self.register_host(a)  # persistent result matrices: the engine DMAs straight into them
         return cache[key]
+
+    def register_host(self, arr: np.ndarray):
+        """b200jk_register_host: page-lock a persistent caller array (D, J, K, wK) for direct DMA.  The array must
+        outlive the engine or be unregistered first."""
+        self._check(self.L.b200jk_register_host(self.h, ct.c_void_p(arr.ctypes.data), arr.nbytes))
+        self.__dict__.setdefault("_registered", []).append(arr)  # keep it alive
+
+    def unregister_host(self, arr: np.ndarray):
+        self._check(self.L.b200jk_unregister_host(self.h, ct.c_void_p(arr.ctypes.data)))
 
     def compute(self, Cl, Cr, D, do_J=True, do_K=True, do_wK=False, reuse_outputs=False):
         """Host-operand build.  Cl/Cr: lists of (nbf, nocc_i) arrays (Cr None => lr_symmetric);

@@ -329,3 +329,26 @@ def test_oom_is_an_error_not_a_fallback():
         e.fill_synthetic(0, 1, np.ones((n, n)))
     assert ei.value.code == 3  # B200JK_ERR_OOM
     e.close()
+
+
+def test_registered_host_buffers_same_result(oracle):
+    """b200jk_register_host: D/J/K in page-locked caller memory are DMA'd in place; results identical to staging."""
+    from psi4_b200 import Engine
+
+    rng = np.random.default_rng(31)
+    n, a, o = 80, 50, 11
+    keep = random_mask(rng, n, 0.7)
+    sp, d, B, P = make(oracle, rng, n, a, keep, 0.2)
+    C = rng.standard_normal((n, o))
+    D = C @ C.T
+    e = Engine(1)
+    e.set_layout(n, a, d.small_skips_, d.big_skips_, d.schwarz_fun_index_)
+    e.upload(0, P)
+    J0, K0, _ = e.compute([C], None, [D])
+    e.register_host(D)
+    J1, K1, _ = e.compute([C], None, [D], reuse_outputs=True)  # persistent, registered outputs
+    assert np.array_equal(J0[0], J1[0]) and np.array_equal(K0[0], K1[0])
+    J2, K2, _ = e.compute([2 * C], None, [4 * D], reuse_outputs=True)  # 4*D is a fresh unregistered array -> staged
+    assert J2[0] is J1[0] and np.array_equal(J2[0], 4 * J0[0]) and np.array_equal(K2[0], 4 * K0[0])
+    e.unregister_host(D)
+    e.close()
