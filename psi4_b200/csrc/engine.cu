@@ -196,6 +196,7 @@ int grow(b200jk* h, double** p, size_t* cap, size_t need) {
 cudaEvent_t get_event(Shard& s) {
     if (s.evused == s.evpool.size()) {
         cudaEvent_t e;
+        cudaSetDevice(s.dev);  // events belong to the device that is current when they are created
         cudaEventCreate(&e);
         s.evpool.push_back(e);
     }
