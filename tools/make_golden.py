@@ -63,6 +63,18 @@ anchors = {
         "triplet_uhf_df": grab("scf5/input.dat", r'"Triplet UHF": \{\s*"Canonical" : -?\d+\.\d+, #TEST\s*"DF"\s*: (-\d+\.\d+)'),
         "tolerance_decimals": 6,
     },
+    "dlpnocc4_decane_def2svp": {
+        "source": "tests/dlpnocc-4/input.dat:4,26-62,64-72,84 ; output.ref:259,283,310-312,319,344-358",
+        "basis": "def2-svp", "aux": "def2-universal-jkfit",
+        "scf_total_energy": grab("dlpnocc-4/input.dat", r"ref_scf\s+=\s+(-\d+\.\d+)"),
+        "tolerance_decimals": 7,
+        "nuclear_repulsion_output_ref": grab("dlpnocc-4/output.ref", r"Nuclear repulsion =\s+(\d+\.\d+)"),
+        "mask_sparsity_percent_output_ref": grab("dlpnocc-4/output.ref", r"Mask sparsity \(%\):\s+(\d+\.\d+)"),
+        "final_iteration_energy_output_ref": grab("dlpnocc-4/output.ref", r"@DF-RHF iter\s+14:\s+(-\d+\.\d+)"),
+        "nbf": 250, "naux": 1146,
+        "geometry_angstrom_input": [[l.split()[0]] + [float(x) for x in l.split()[1:4]]
+                                    for l in open(os.path.join(REF, "dlpnocc-4/input.dat")).read().split("0 1\n")[1].split("units")[0].strip().splitlines()],
+    },
     "dfscf_bz2_ccpvdz": {
         "source": "tests/dfscf-bz2/input.dat:3-4,50-56 ; output.ref (geometry block, :149)",
         "basis": "cc-pvdz", "aux": "cc-pvdz-jkfit",
