@@ -98,3 +98,34 @@ def test_one_process_per_gpu_torchrun(tmp_path):
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "RANK0 err=" in r.stdout and "RANK1 err=" in r.stdout
+
+
+LEGACY_SCRIPT = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.environ["B2_ROOT"]); sys.path.insert(0, os.path.join(os.environ["B2_ROOT"], "oracle"))
+import dfjk_oracle as oracle
+from psi4_b200 import DFHelper, Engine
+rng = np.random.default_rng(3)
+n, a, o = 140, 150, 21
+r = rng.random((n, n)); keep = (r + r.T) < 1.3; np.fill_diagonal(keep, True)
+d = DFHelper(n, a); d.prepare_sparsity(keep=keep)
+B = rng.standard_normal((a, n, n)) * 0.1; B = B + B.transpose(0, 2, 1)
+P = d.pack(B); C = rng.standard_normal((n, o))
+e = Engine(1); e.set_layout(n, a, d.small_skips_, d.big_skips_, d.schwarz_fun_index_); e.upload(0, P)
+J, K, _ = e.compute([C], None, [C @ C.T])
+Jo, Ko, _, _ = oracle.build_JK(oracle.Sparsity(keep, a), P, [C])
+err = max(np.abs(J[0] - Jo[0]).max(), np.abs(K[0] - Ko[0]).max())
+print(f"LEGACY={os.environ.get('B200JK_LEGACY')} NOFUSE={os.environ.get('B200JK_NO_JFUSE')} err={err:.3e}")
+assert err < 1e-10
+"""
+
+
+@pytest.mark.parametrize("env", [{"B200JK_LEGACY": "1"}, {"B200JK_NO_JFUSE": "1"}])
+def test_ab_switches_still_correct(tmp_path, env):
+    """The A/B switches documented in DESIGN.md (first-generation kernels, unfused J) stay parity-green."""
+    script = tmp_path / "ab.py"
+    script.write_text(LEGACY_SCRIPT)
+    r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, B2_ROOT=ROOT, **env), capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
