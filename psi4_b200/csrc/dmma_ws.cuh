@@ -31,7 +31,7 @@
 
 namespace b2k {
 
-constexpr int WS_STAGES = 6;
+constexpr int WS_STAGES = 6;  // 7 stages fit as well but measured no faster: the ring is not latency-bound
 constexpr int WS_CONSUMER_WARPS = 8;
 constexpr int WS_PRODUCER_WARPS = 4;   // one warpgroup (setmaxnreg works per warpgroup)
 constexpr int WS_PRODUCER_THREADS = 32 * WS_PRODUCER_WARPS;
@@ -83,6 +83,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(addr), "r"(parity)
             : "memory");
     } while (!ok);
+}
+// Non-blocking probe of a phase (consumers look one stage ahead so that the probe's latency overlaps their DMMAs).
+__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok;
+}
+// Producer-side wait: the producer is normally several stages ahead and would otherwise spin on try_wait every few
+// tens of cycles, stealing issue slots from the two consumer warps that share its SM sub-partition.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar), ok;
+    for (;;) {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) break;
+        __nanosleep(160);
+    }
 }
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
@@ -271,7 +295,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
                     for (int kt = 0; kt < nkt; kt++) {
                         const uint32_t gg = g + kt;
                         const int s = gg % WS_STAGES;
-                        mbar_wait(&sm.empty[s], ((gg / WS_STAGES) & 1) ^ 1);
+                        mbar_wait_backoff(&sm.empty[s], ((gg / WS_STAGES) & 1) ^ 1);
                         if (kt == 0) sm.meta[s] = w;
                         if (!fused) {
                             mbar_arrive_expect_tx(&sm.full[s], WS_A_STAGE + B_STAGE);
@@ -326,7 +350,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         }
         if (tid == 0) {  // sentinel stage: tells every consumer warp to stop
             const int s = g % WS_STAGES;
-            mbar_wait(&sm.empty[s], ((g / WS_STAGES) & 1) ^ 1);
+            mbar_wait_backoff(&sm.empty[s], ((g / WS_STAGES) & 1) ^ 1);
             sm.meta[s] = -1;
             mbar_arrive_n(&sm.full[s], 1 + WS_PRODUCER_THREADS);
         }
@@ -365,11 +389,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
 #pragma unroll
             for (int b = 0; b < NB; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
 
+        uint32_t ready = 1;  // the stage of kt = 0 was awaited above
         for (int kt = 0; kt < nkt; kt++, g++) {
             if (kt > 0) {
                 s = g % WS_STAGES;
-                mbar_wait(&sm.full[s], (g / WS_STAGES) & 1);
+                if (!ready) mbar_wait(&sm.full[s], (g / WS_STAGES) & 1);
             }
+            // probe the NEXT stage now: the probe's latency hides under this stage's DMMAs
+            ready = (kt + 1 < nkt) ? mbar_test(&sm.full[(g + 1) % WS_STAGES], ((g + 1) / WS_STAGES) & 1) : 0;
             const uint8_t* a_row = sm.As + s * WS_A_STAGE + a_row0;
             const uint8_t* b_row = sm.Bs + s * B_STAGE + b_row0;
             mma_stage_any<NB>(a_row, b_row, off, acc, mbv, nbv);
@@ -443,7 +470,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
                 const int nkt = (ke - kb + BK - 1) / BK;
                 for (int kt = 0; kt < nkt; kt++, g++) {
                     const int s = g % WS_STAGES;
-                    mbar_wait(&sm.empty[s], ((g / WS_STAGES) & 1) ^ 1);
+                    mbar_wait_backoff(&sm.empty[s], ((g / WS_STAGES) & 1) ^ 1);
                     if (kt == 0) sm.meta[s] = w;
                     mbar_arrive_expect_tx(&sm.full[s], WS_A_STAGE + B_STAGE);
                     tma_load_2d(sm.As + s * WS_A_STAGE, &t1map, kb + kt * BK, tl.x * BM, &sm.full[s]);
@@ -452,7 +479,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
                 w = w_next;
             }
             const int s = g % WS_STAGES;
-            mbar_wait(&sm.empty[s], ((g / WS_STAGES) & 1) ^ 1);
+            mbar_wait_backoff(&sm.empty[s], ((g / WS_STAGES) & 1) ^ 1);
             sm.meta[s] = -1;
             mbar_arrive(&sm.full[s]);
         }
@@ -485,11 +512,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         for (int a = 0; a < 4; a++)
 #pragma unroll
             for (int b = 0; b < NB; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+        uint32_t ready = 1;
         for (int kt = 0; kt < nkt; kt++, g++) {
             if (kt > 0) {
                 s = g % WS_STAGES;
-                mbar_wait(&sm.full[s], (g / WS_STAGES) & 1);
+                if (!ready) mbar_wait(&sm.full[s], (g / WS_STAGES) & 1);
             }
+            ready = (kt + 1 < nkt) ? mbar_test(&sm.full[(g + 1) % WS_STAGES], ((g + 1) / WS_STAGES) & 1) : 0;
             const uint8_t* a_row = sm.As + s * WS_A_STAGE + a_row0;
             const uint8_t* b_row = sm.Bs + s * B_STAGE + b_row0;
             mma_stage_any<NB>(a_row, b_row, off, acc, mbv, nbv);
@@ -553,7 +582,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
                 const int tm = w % p.ntm, tn = w / p.ntm;  // q tiles fastest: CTAs in flight share the U tile
                 for (int kt = 0; kt < nkt; kt++, g++) {
                     const int s = g % WS_STAGES;
-                    mbar_wait(&sm.empty[s], ((g / WS_STAGES) & 1) ^ 1);
+                    mbar_wait_backoff(&sm.empty[s], ((g / WS_STAGES) & 1) ^ 1);
                     if (kt == 0) sm.meta[s] = w;
                     mbar_arrive_expect_tx(&sm.full[s], WS_A_STAGE + B_STAGE);
                     tma_load_2d(sm.As + s * WS_A_STAGE, &metmap, kt * BK, tm * BM, &sm.full[s]);
@@ -562,7 +591,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
                 w = w_next;
             }
             const int s = g % WS_STAGES;
-            mbar_wait(&sm.empty[s], ((g / WS_STAGES) & 1) ^ 1);
+            mbar_wait_backoff(&sm.empty[s], ((g / WS_STAGES) & 1) ^ 1);
             sm.meta[s] = -1;
             mbar_arrive(&sm.full[s]);
         }
@@ -591,11 +620,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         for (int a = 0; a < 4; a++)
 #pragma unroll
             for (int b = 0; b < NB; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+        uint32_t ready = 1;
         for (int kt = 0; kt < nkt; kt++, g++) {
             if (kt > 0) {
                 s = g % WS_STAGES;
-                mbar_wait(&sm.full[s], (g / WS_STAGES) & 1);
+                if (!ready) mbar_wait(&sm.full[s], (g / WS_STAGES) & 1);
             }
+            ready = (kt + 1 < nkt) ? mbar_test(&sm.full[(g + 1) % WS_STAGES], ((g + 1) / WS_STAGES) & 1) : 0;
             mma_stage_any<NB>(sm.As + s * WS_A_STAGE + a_row0, sm.Bs + s * B_STAGE + b_row0, off, acc, mbv, nbv);
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.empty[s]);
