@@ -221,6 +221,107 @@ __device__ __forceinline__ WsCarve ws_carve(uint8_t* raw) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Consumer main loop of one work item, specialised at compile time on this warp's live blocks (ML rows x NL columns)
+// and software-pipelined: fragments are double-buffered in registers, the loads of k-step s+1 -- and, on the last
+// k-step of a stage, of the NEXT stage's first k-step -- are issued before the DMMAs of k-step s, and the stage is
+// released as soon as its last fragment has been read.  The two consumer warps of an SM sub-partition run in
+// lock-step (they share the pipe and the stage ring), so without this the barrier-probe / address / LDS latency at
+// the top of every stage left the DMMA pipe idle (~6 % in K3).
+// Entry: the caller has waited for full[g % WS_STAGES].  Exit: g advanced by nkt.
+// ---------------------------------------------------------------------------------------------
+template <int NB, int ML, int NL>
+__device__ __forceinline__ void consume_item(const WsCarve& sm, int b_stage_bytes, int a_row0, int b_row0,
+                                             const int (&off)[4], double (&acc)[4][NB][2], int nkt, uint32_t& g, int lane) {
+    if constexpr (ML == 0 || NL == 0) {
+        // nothing to compute in this warp's corner of the tile: keep the ring protocol going
+        for (int kt = 0; kt < nkt; kt++, g++) {
+            const int s = g % WS_STAGES;
+            if (kt > 0) mbar_wait(&sm.full[s], (g / WS_STAGES) & 1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[s]);
+        }
+    } else {
+        double a[2][ML], b[2][NL];
+        int s = g % WS_STAGES;
+        const uint8_t* ap = sm.As + s * WS_A_STAGE + a_row0;
+        const uint8_t* bp = sm.Bs + s * b_stage_bytes + b_row0;
+#pragma unroll
+        for (int mb = 0; mb < ML; mb++) a[0][mb] = *reinterpret_cast<const double*>(ap + mb * WS_A_MB_STRIDE + off[0]);
+#pragma unroll
+        for (int nb = 0; nb < NL; nb++) b[0][nb] = *reinterpret_cast<const double*>(bp + nb * 8 * WS_ROW_BYTES + off[0]);
+        for (int kt = 0; kt < nkt; kt++, g++) {
+            const bool has_next = kt + 1 < nkt;
+            const int sn = (g + 1) % WS_STAGES;
+            const uint32_t pn = ((g + 1) / WS_STAGES) & 1;
+            const uint32_t ready = has_next ? mbar_test(&sm.full[sn], pn) : 0;
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) {
+                const int cur = ks & 1, nxt = cur ^ 1;
+                if (ks < 3) {
+#pragma unroll
+                    for (int mb = 0; mb < ML; mb++)
+                        a[nxt][mb] = *reinterpret_cast<const double*>(ap + mb * WS_A_MB_STRIDE + off[ks + 1]);
+#pragma unroll
+                    for (int nb = 0; nb < NL; nb++)
+                        b[nxt][nb] = *reinterpret_cast<const double*>(bp + nb * 8 * WS_ROW_BYTES + off[ks + 1]);
+                } else {
+                    // every fragment of this stage has been read: hand it back, then reach into the next stage
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.empty[g % WS_STAGES]);
+                    if (has_next) {
+                        if (!ready) mbar_wait(&sm.full[sn], pn);
+                        ap = sm.As + sn * WS_A_STAGE + a_row0;
+                        bp = sm.Bs + sn * b_stage_bytes + b_row0;
+#pragma unroll
+                        for (int mb = 0; mb < ML; mb++)
+                            a[nxt][mb] = *reinterpret_cast<const double*>(ap + mb * WS_A_MB_STRIDE + off[0]);
+#pragma unroll
+                        for (int nb = 0; nb < NL; nb++)
+                            b[nxt][nb] = *reinterpret_cast<const double*>(bp + nb * 8 * WS_ROW_BYTES + off[0]);
+                    }
+                }
+#pragma unroll
+                for (int mb = 0; mb < ML; mb++)
+#pragma unroll
+                    for (int nb = 0; nb < NL; nb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[cur][mb], b[cur][nb]);
+            }
+        }
+    }
+}
+template <int NB, int ML, int NL>
+struct ItemDispatchN {
+    static __device__ __forceinline__ void run(const WsCarve& sm, int bsb, int a_row0, int b_row0, const int (&off)[4],
+                                               double (&acc)[4][NB][2], int nkt, uint32_t& g, int lane, int nbv) {
+        if (nbv == NL)
+            consume_item<NB, ML, NL>(sm, bsb, a_row0, b_row0, off, acc, nkt, g, lane);
+        else
+            ItemDispatchN<NB, ML, NL - 1>::run(sm, bsb, a_row0, b_row0, off, acc, nkt, g, lane, nbv);
+    }
+};
+template <int NB, int ML>
+struct ItemDispatchN<NB, ML, 0> {
+    static __device__ __forceinline__ void run(const WsCarve& sm, int bsb, int a_row0, int b_row0, const int (&off)[4],
+                                               double (&acc)[4][NB][2], int nkt, uint32_t& g, int lane, int) {
+        consume_item<NB, 0, 0>(sm, bsb, a_row0, b_row0, off, acc, nkt, g, lane);
+    }
+};
+// mbv / nbv are warp-uniform and constant over the item: one dispatch per item, not per stage.
+template <int NB>
+__device__ __forceinline__ void consume_item_any(const WsCarve& sm, int bsb, int a_row0, int b_row0, const int (&off)[4],
+                                                 double (&acc)[4][NB][2], int nkt, uint32_t& g, int lane, int mbv, int nbv) {
+    if (mbv == 4)
+        ItemDispatchN<NB, 4, NB>::run(sm, bsb, a_row0, b_row0, off, acc, nkt, g, lane, nbv);
+    else if (mbv == 3)
+        ItemDispatchN<NB, 3, NB>::run(sm, bsb, a_row0, b_row0, off, acc, nkt, g, lane, nbv);
+    else if (mbv == 2)
+        ItemDispatchN<NB, 2, NB>::run(sm, bsb, a_row0, b_row0, off, acc, nkt, g, lane, nbv);
+    else if (mbv == 1)
+        ItemDispatchN<NB, 1, NB>::run(sm, bsb, a_row0, b_row0, off, acc, nkt, g, lane, nbv);
+    else
+        consume_item<NB, 0, 0>(sm, bsb, a_row0, b_row0, off, acc, nkt, g, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
 // K3, persistent.  Work item w -> (it, qt, m): it fastest so the CTAs sharing an A tile run together.
 // ---------------------------------------------------------------------------------------------
 struct HalfWsParams {
@@ -389,20 +490,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
 #pragma unroll
             for (int b = 0; b < NB; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-        uint32_t ready = 1;  // the stage of kt = 0 was awaited above
-        for (int kt = 0; kt < nkt; kt++, g++) {
-            if (kt > 0) {
-                s = g % WS_STAGES;
-                if (!ready) mbar_wait(&sm.full[s], (g / WS_STAGES) & 1);
-            }
-            // probe the NEXT stage now: the probe's latency hides under this stage's DMMAs
-            ready = (kt + 1 < nkt) ? mbar_test(&sm.full[(g + 1) % WS_STAGES], ((g + 1) / WS_STAGES) & 1) : 0;
-            const uint8_t* a_row = sm.As + s * WS_A_STAGE + a_row0;
-            const uint8_t* b_row = sm.Bs + s * B_STAGE + b_row0;
-            mma_stage_any<NB>(a_row, b_row, off, acc, mbv, nbv);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.empty[s]);
-        }
+        consume_item_any<NB>(sm, B_STAGE, a_row0, b_row0, off, acc, nkt, g, lane, mbv, nbv);
 
         double* Tm = p.T + (size_t)m * p.qc * p.op;
 #pragma unroll
@@ -512,19 +600,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         for (int a = 0; a < 4; a++)
 #pragma unroll
             for (int b = 0; b < NB; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
-        uint32_t ready = 1;
-        for (int kt = 0; kt < nkt; kt++, g++) {
-            if (kt > 0) {
-                s = g % WS_STAGES;
-                if (!ready) mbar_wait(&sm.full[s], (g / WS_STAGES) & 1);
-            }
-            ready = (kt + 1 < nkt) ? mbar_test(&sm.full[(g + 1) % WS_STAGES], ((g + 1) / WS_STAGES) & 1) : 0;
-            const uint8_t* a_row = sm.As + s * WS_A_STAGE + a_row0;
-            const uint8_t* b_row = sm.Bs + s * B_STAGE + b_row0;
-            mma_stage_any<NB>(a_row, b_row, off, acc, mbv, nbv);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.empty[s]);
-        }
+        consume_item_any<NB>(sm, B_STAGE, a_row0, b_row0, off, acc, nkt, g, lane, mbv, nbv);
         double* wsp = p.ws + (size_t)w * (BM * BN);
 #pragma unroll
         for (int mb = 0; mb < 4; mb++) {
@@ -620,17 +696,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         for (int a = 0; a < 4; a++)
 #pragma unroll
             for (int b = 0; b < NB; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
-        uint32_t ready = 1;
-        for (int kt = 0; kt < nkt; kt++, g++) {
-            if (kt > 0) {
-                s = g % WS_STAGES;
-                if (!ready) mbar_wait(&sm.full[s], (g / WS_STAGES) & 1);
-            }
-            ready = (kt + 1 < nkt) ? mbar_test(&sm.full[(g + 1) % WS_STAGES], ((g + 1) / WS_STAGES) & 1) : 0;
-            mma_stage_any<NB>(sm.As + s * WS_A_STAGE + a_row0, sm.Bs + s * B_STAGE + b_row0, off, acc, mbv, nbv);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.empty[s]);
-        }
+        consume_item_any<NB>(sm, B_STAGE, a_row0, b_row0, off, acc, nkt, g, lane, mbv, nbv);
 #pragma unroll
         for (int nb = 0; nb < NB; nb++) {
             const int j0 = tn * BN + wn * 8 * NB + nb * 8 + t * 2;
