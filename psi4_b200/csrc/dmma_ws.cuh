@@ -122,82 +122,6 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(map) : "memory");
 }
 
-// One stage (16 k) of DMMAs from swizzled tiles.  a_row / b_row point at this lane's first fragment
-// row (row & 7 == g); off[s] is the lane's swizzled byte offset for k-step s.
-template <int NB, bool FULL>
-__device__ __forceinline__ void mma_stage_swz(const uint8_t* __restrict__ a_row, const uint8_t* __restrict__ b_row,
-                                              const int (&off)[4], double (&acc)[4][NB][2], int mbv, int nbv) {
-#pragma unroll
-    for (int ks = 0; ks < 4; ks++) {
-        double a[4], b[NB];
-#pragma unroll
-        for (int mb = 0; mb < 4; mb++) a[mb] = *reinterpret_cast<const double*>(a_row + mb * WS_A_MB_STRIDE + off[ks]);
-#pragma unroll
-        for (int nb = 0; nb < NB; nb++) b[nb] = *reinterpret_cast<const double*>(b_row + nb * 8 * WS_ROW_BYTES + off[ks]);
-        if (FULL) {
-#pragma unroll
-            for (int mb = 0; mb < 4; mb++)
-#pragma unroll
-                for (int nb = 0; nb < NB; nb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
-        } else {
-#pragma unroll
-            for (int mb = 0; mb < 4; mb++) {
-                if (mb < mbv) {
-#pragma unroll
-                    for (int nb = 0; nb < NB; nb++)
-                        if (nb < nbv) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
-                }
-            }
-        }
-    }
-}
-
-// Unpredicated stage for a warp with exactly MLIVE live 8-row blocks and LIVE live 8-column blocks, both compile-time
-// (a predicated mma.sync costs a WARPSYNC + branch per DMMA and one slow warp gates the whole stage ring).
-template <int NB, int MLIVE, int LIVE>
-__device__ __forceinline__ void mma_stage_ml(const uint8_t* __restrict__ a_row, const uint8_t* __restrict__ b_row,
-                                             const int (&off)[4], double (&acc)[4][NB][2]) {
-#pragma unroll
-    for (int ks = 0; ks < 4; ks++) {
-        double a[MLIVE], b[LIVE];
-#pragma unroll
-        for (int mb = 0; mb < MLIVE; mb++) a[mb] = *reinterpret_cast<const double*>(a_row + mb * WS_A_MB_STRIDE + off[ks]);
-#pragma unroll
-        for (int nb = 0; nb < LIVE; nb++) b[nb] = *reinterpret_cast<const double*>(b_row + nb * 8 * WS_ROW_BYTES + off[ks]);
-#pragma unroll
-        for (int mb = 0; mb < MLIVE; mb++)
-#pragma unroll
-            for (int nb = 0; nb < LIVE; nb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
-    }
-}
-template <int NB, int MLIVE, int LIVE>
-struct StageDispatchN {
-    static __device__ __forceinline__ void run(const uint8_t* a_row, const uint8_t* b_row, const int (&off)[4],
-                                               double (&acc)[4][NB][2], int nbv) {
-        if (nbv == LIVE)
-            mma_stage_ml<NB, MLIVE, LIVE>(a_row, b_row, off, acc);
-        else
-            StageDispatchN<NB, MLIVE, LIVE - 1>::run(a_row, b_row, off, acc, nbv);
-    }
-};
-template <int NB, int MLIVE>
-struct StageDispatchN<NB, MLIVE, 0> {
-    static __device__ __forceinline__ void run(const uint8_t*, const uint8_t*, const int (&)[4], double (&)[4][NB][2], int) {}
-};
-// mbv / nbv are warp-uniform: every (rows, columns) combination of live blocks has its own unpredicated stream.
-template <int NB>
-__device__ __forceinline__ void mma_stage_any(const uint8_t* a_row, const uint8_t* b_row, const int (&off)[4],
-                                              double (&acc)[4][NB][2], int mbv, int nbv) {
-    if (mbv == 4)
-        StageDispatchN<NB, 4, NB>::run(a_row, b_row, off, acc, nbv);
-    else if (mbv == 3)
-        StageDispatchN<NB, 3, NB>::run(a_row, b_row, off, acc, nbv);
-    else if (mbv == 2)
-        StageDispatchN<NB, 2, NB>::run(a_row, b_row, off, acc, nbv);
-    else if (mbv == 1)
-        StageDispatchN<NB, 1, NB>::run(a_row, b_row, off, acc, nbv);
-}
-
 struct WsCarve {
     uint8_t* As;
     uint8_t* Bs;
