@@ -135,7 +135,7 @@ def main():
 
     cfg = dict(workloads.CONFIGS[args.workload])
     nbf, naux, nocc, nmat = cfg["nbf"], cfg["naux"], cfg["nocc"], cfg["nmat"]
-    keep = workloads.pair_mask(nbf, cfg["band"])
+    keep = workloads.pair_mask(nbf, cfg["mask"])
     amp = workloads.amplitude(nbf)
     C = workloads.orbitals(nbf, nocc)
     Cr = workloads.orbitals(nbf, nocc, workloads.SEED + 1) if args.nonsymmetric else None
@@ -144,6 +144,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": f"{args.workload}: nbf={nbf} naux={naux} nocc={nocc} nmat={nmat} "
                           f"kept_pairs={int(keep.sum())} lr_symmetric={Cr is None} do_J=1 do_K=1",
+              "pair_mask": workloads.mask_info(cfg["mask"]),
               "q_sharding": f"Q split over {world} rank(s)", "l2": "inputs_exceed_l2 (tensor shard >> 126 MB)"}
 
     if args.impl == "reference":

@@ -196,7 +196,7 @@ def test_device_synthetic_fill_bit_exact(oracle):
     from psi4_b200 import Engine, workloads
 
     n, a = 50, 37
-    keep = workloads.pair_mask(n, 0.5, block=5)
+    keep = workloads.banded_mask(n, 0.5, block=5)
     sp = oracle.Sparsity(keep, a)
     amp = workloads.amplitude(n)
     ref = oracle.synth_fill(sp, 0, a, 4242, amp)
