@@ -1,5 +1,5 @@
-"""Full-size checks at the BASELINE.json headline configuration (C60 / cc-pVTZ shape: nbf 1800, naux 4740,
-nocc 180; 122.9 GB packed tensor resident on one B200).  No host copy of that tensor can exist, so:
+"""Full-size checks at the BASELINE.json headline configuration (C60 / cc-pVTZ: nbf 1800, naux 4740, nocc 180, the
+real 28.5 %-sparse Schwarz mask; 87.8 GB packed tensor resident on one B200).  No host copy of that tensor can exist, so:
 
   * spot parity: the synthetic tensor is a counter hash, so the oracle regenerates any row-block on the fly;
     whole rows of J and a sample of K elements are recomputed on the host in float64 and compared;
