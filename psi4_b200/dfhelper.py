@@ -20,6 +20,7 @@ class DFHelper:
         self.cutoff_ = 1e-12  # dfhelper.h: schwarz cutoff default; JK passes INTS_TOLERANCE (jk.cc:58-68)
         self.sparsity_prepared_ = False
         self.do_wK_ = False
+        self.Qshell_max_ = 0  # largest auxiliary shell, prepare_blocking dfhelper.cc:84-103
 
     # ---- knobs (dfhelper.h:100-175) ----
     def set_schwarz_cutoff(self, cutoff: float):
@@ -30,6 +31,10 @@ class DFHelper:
 
     def set_do_wK(self, do_wK: bool):
         self.do_wK_ = bool(do_wK)
+
+    def set_Qshell_max(self, qshell_max: int):
+        """Qshell_max_ of prepare_blocking (dfhelper.cc:84-103): functions in the largest auxiliary shell."""
+        self.Qshell_max_ = int(qshell_max)
 
     # ---- dfhelper.cc:371-416 ----
     def prepare_sparsity(self, fun_max_vals: np.ndarray | None = None, keep: np.ndarray | None = None):
@@ -61,8 +66,10 @@ class DFHelper:
         """dfhelper.h:101  fraction of screened pairs."""
         return 1.0 - float(self.small_skips_[self.nbf_]) / float(self.nbf_ * self.nbf_)
 
-    def get_core_size(self, nthreads: int = 1, qshell_max: int = 0) -> int:
+    def get_core_size(self, nthreads: int = 1, qshell_max: int | None = None) -> int:
         """dfhelper.cc:216-236 required_core_size_ in doubles (host model; Qshell_max needs the aux shells)."""
+        if qshell_max is None:
+            qshell_max = self.Qshell_max_
         big = int(self.big_skips_[self.nbf_])
         req = 3 * big if self.do_wK_ else big
         req += self.naux_ * self.naux_

@@ -21,8 +21,8 @@ BOHR_TO_ANGSTROM = 0.52917721067
 _HERE = os.path.dirname(os.path.abspath(__file__))
 BASIS_DIR = os.path.join(_HERE, "share", "basis")
 INTS_LIB_PATH = os.path.join(_HERE, "libb200ints.so")
-Z_OF = {"H": 1, "HE": 2, "LI": 3, "BE": 4, "B": 5, "C": 6, "N": 7, "O": 8, "F": 9, "NE": 10}
-L_OF = {"S": 0, "P": 1, "D": 2, "F": 3, "G": 4, "H": 5}
+Z_OF = {"H": 1, "HE": 2, "LI": 3, "BE": 4, "B": 5, "C": 6, "N": 7, "O": 8, "F": 9, "NE": 10, "AR": 18}
+L_OF = {"S": 0, "P": 1, "D": 2, "F": 3, "G": 4, "H": 5, "I": 6}
 
 _lib = None
 
@@ -107,6 +107,21 @@ def parse_gbs(name: str) -> tuple[bool, dict]:
             i += 1 + nprim
         out[elem] = shells
     return spherical, out
+
+
+def basis_shape(mol: "Molecule", name: str, puream: bool | None = None) -> tuple[int, int]:
+    """(number of functions, largest shell) of a basis on a molecule without building any integral: all that
+    DFHelper::get_core_size (dfhelper.cc:216-236) needs from the auxiliary basis (naux_, Qshell_max_)."""
+    spherical, table = parse_gbs(name)
+    if puream is not None:
+        spherical = puream
+    nf = lambda l: 2 * l + 1 if spherical else (l + 1) * (l + 2) // 2  # noqa: E731
+    tot, big = 0, 0
+    for sym in mol.symbols:
+        for l, _, _ in table[sym.upper()]:
+            tot += nf(l)
+            big = max(big, nf(l))
+    return tot, big
 
 
 def _dfact(n):

@@ -138,3 +138,30 @@ def test_engine_refuses_without_gpu():
     with pytest.raises(b2lib.B200JKError) as e:
         b2lib.Engine(1)
     assert e.value.code == 5  # B200JK_ERR_NODEVICE: no CPU fallback
+
+
+@pytest.mark.parametrize("basis", ["cc-pvdz", "cc-pv5z"])
+def test_memory_estimate_matches_reference_integers(basis):
+    """tests/pytests/test_jkmemory.py:44,49 -- jk.memory_estimate() of MEM_DF for five Ar atoms on a line
+    (1 590 520 and 57 020 770 doubles): pins prepare_sparsity's mask (Schwarz integrals up to h functions, cutoff
+    1e-12, dfhelper.cc:371-386), big_skips_ (:390-397), naux_ / Qshell_max_ and DFHelper::get_core_size (:216-236)
+    as exact integers."""
+    import json
+    import os
+
+    from psi4_b200 import MemDFJK
+    from psi4_b200.dfhelper import DFHelper
+    from psi4_b200.integrals import BasisSet, MintsHelper, Molecule, basis_shape
+
+    a = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_anchors.json")))["jkmemory_ar5"]
+    mol = Molecule.from_angstrom([g[0] for g in a["geometry_angstrom"]], [g[1:] for g in a["geometry_angstrom"]])
+    P = BasisSet.build(mol, basis)
+    naux, qshell_max = basis_shape(mol, basis + "-jkfit", puream=True)
+    dfh = DFHelper(P.nbf(), naux)
+    dfh.set_Qshell_max(qshell_max)
+    dfh.prepare_sparsity(MintsHelper(mol, P).schwarz_function_maxima())
+    jk = MemDFJK(dfh)           # no tensor, no device: memory_estimate is host logic (MemDFJK.cc:65-69)
+    jk.set_omp_nthread(1)       # "ref valid for -n1 only", test_jkmemory.py:35
+    jk.set_do_wK(False)
+    assert jk.name() == "MemDFJK"
+    assert jk.memory_estimate() == a["mem_df_estimate_doubles"][basis]

@@ -7,8 +7,10 @@ import sys
 SRC = "/root/reference/psi4/share/psi4/basis"
 DST = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "psi4_b200", "share", "basis")
 WANT = {
-    "cc-pvdz": ["H", "C", "N", "O"],
-    "cc-pvdz-jkfit": ["H", "C", "N", "O"],
+    "cc-pvdz": ["H", "C", "N", "O", "Ar"],
+    "cc-pvdz-jkfit": ["H", "C", "N", "O", "Ar"],
+    "cc-pv5z": ["Ar"],
+    "cc-pv5z-jkfit": ["Ar"],
     "cc-pvtz": ["H", "C", "O"],
     "cc-pvtz-jkfit": ["H", "C", "O"],
     "aug-cc-pvdz": ["H", "C", "O"],

@@ -84,6 +84,14 @@ anchors = {
         "geometry_angstrom_output_ref": geometry_block("dfscf-bz2/output.ref"),
         "nbf": 228, "naux": 1116,
     },
+    "jkmemory_ar5": {
+        "source": "tests/pytests/test_jkmemory.py:12-18,44,49 (MEM_DF rows, one thread, memory=1e9, do_wK=False)",
+        "geometry_angstrom": [["Ar", 0.0, 0.0, z] for z in (0.0, 5.0, 15.0, 25.0, 35.0)],
+        "mem_df_estimate_doubles": {
+            "cc-pvdz": grab("pytests/test_jkmemory.py", r'\["cc-pvdz", "MEM_DF",\s+(\d+)', int),
+            "cc-pv5z": grab("pytests/test_jkmemory.py", r'\["cc-pv5z", "MEM_DF",\s+(\d+)', int),
+        },
+    },
 }
 json.dump(anchors, open(OUT, "w"), indent=1)
 print(OUT, {k: (v.get("scf_total_energy") or v.get("scf_energy") or v.get("singlet_rhf_df")) for k, v in anchors.items() if isinstance(v, dict)})
