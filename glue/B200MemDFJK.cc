@@ -80,31 +80,37 @@ void B200MemDFJK::preiterations() {
     timer_on("JK: B200 upload");
     std::static_pointer_cast<B200DFHelper>(dfh_)->move_to_device(handle_, release_host_);
     timer_off("JK: B200 upload");
-    registered_ = false;
 }
 
 void B200MemDFJK::register_persistent_matrices() {
     // D_ao_/J_ao_/K_ao_/wK_ao_ are allocated once by JK::allocate_JK / USO2AO (jk.cc:355-446) and reused by every
-    // compute(); page-locking them lets the engine DMA in place.  A changed matrix count re-allocates them, so
-    // compute_JK re-registers when a pointer is not known yet (registering twice is a no-op in the engine).
+    // compute(); page-locking them lets the engine DMA in place.  When the matrix count changes psi4 re-allocates
+    // them, so the set of pointers is compared on every build: vanished ones are unregistered, new ones registered
+    // (anything left unregistered is simply staged through the engine's pinned buffers).
     // (sizes from the matrices themselves: basisset.h pulls in <libint2/shell.h>, which this file does not need)
-    auto reg = [&](std::vector<SharedMatrix>& v) {
-        for (auto& m : v) {
-            if (!m) continue;
-            const size_t bytes = sizeof(double) * m->rowspi()[0] * m->colspi()[0];
-            if (b200jk_register_host(handle_, m->get_pointer(), bytes) != B200JK_OK) fail("register_host");
-        }
+    std::vector<std::pair<double*, size_t>> now;
+    auto collect = [&](std::vector<SharedMatrix>& v) {
+        for (auto& m : v)
+            if (m) now.push_back({m->get_pointer(), sizeof(double) * m->rowspi()[0] * m->colspi()[0]});
     };
-    reg(D_ao_);
-    reg(J_ao_);
-    reg(K_ao_);
-    if (do_wK_) reg(wK_ao_);
-    registered_ = true;
+    collect(D_ao_);
+    if (do_J_) collect(J_ao_);
+    if (do_K_) collect(K_ao_);
+    if (do_wK_) collect(wK_ao_);
+    if (now == pinned_) return;
+    for (auto& old : pinned_) {
+        bool keep = false;
+        for (auto& n : now) keep = keep || n == old;
+        if (!keep) b200jk_unregister_host(handle_, old.first);  // already freed by psi4: best effort
+    }
+    for (auto& n : now)
+        if (b200jk_register_host(handle_, n.first, n.second) != B200JK_OK) fail("register_host");
+    pinned_ = now;
 }
 
 void B200MemDFJK::compute_JK() {
     const int nmat = static_cast<int>(C_left_ao_.size());
-    if (!registered_) register_persistent_matrices();
+    register_persistent_matrices();
 
     std::vector<const double*> Cl(nmat), Cr(nmat), D(nmat);
     std::vector<double*> J(nmat, nullptr), K(nmat, nullptr), wK(nmat, nullptr);

@@ -14,6 +14,7 @@
 
 #include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "psi4/lib3index/dfhelper.h"
@@ -44,7 +45,7 @@ class B200MemDFJK : public MemDFJK {
     b200jk_t* handle_ = nullptr;
     int ngpu_;
     bool release_host_;
-    bool registered_ = false;
+    std::vector<std::pair<double*, size_t>> pinned_;  // page-locked D/J/K/wK matrices
 
     std::string name() override { return "B200MemDFJK"; }
     void preiterations() override;   // MemDFJK.cc:71-96, then upload
