@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-probes", action="store_true", help="no FP64 ceiling probes (ncu launch lists); roofline.peak = last recorded")
     ap.add_argument("--nonsymmetric", action="store_true", help="C_right != C_left (general path)")
+    ap.add_argument("--response", type=int, default=0, metavar="R",
+                    help="R right-hand sides sharing ONE C_left with R different C_right, the shape of the reference's "
+                         "response builds (twoel_Hx, libscf_solver/rhf.cc:466-484); implies --nonsymmetric")
     ap.add_argument("--single-process", action="store_true",
                     help="with --gpus N and no torchrun: one process drives N GPUs (psi4's deployment mode)")
     return ap.parse_args()
@@ -93,7 +96,7 @@ class Clocks:
 # --------------------------------------------------------------------------------------------
 # CPU baseline: the oracle on a Q-slice of the same workload
 # --------------------------------------------------------------------------------------------
-def cpu_baseline(cfg, keep, amp, C, Cr, slice_rows, steps=1, warmup=0):
+def cpu_baseline(cfg, keep, amp, C, Crl, slice_rows, steps=1, warmup=0):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import dfjk_oracle as oracle  # bench.py's cpu_baseline / --impl reference legs may use oracle/
 
@@ -104,14 +107,13 @@ def cpu_baseline(cfg, keep, amp, C, Cr, slice_rows, steps=1, warmup=0):
     oracle.lib().oracle_set_blas_threads(cores)
     if not slice_rows:
         # ~15 s of CPU work at an assumed 25 GFLOP/s/core: K flops per Q row = 2*(P*o) + 2*N^2*o (+ second transform)
-        per_row = (2.0 * keep.sum() * cfg["nocc"] * (1 if Cr is None else 2) + 2.0 * nbf * nbf * cfg["nocc"]) * cfg["nmat"]
+        per_row = (2.0 * keep.sum() * cfg["nocc"] * (1 if Crl is None else 2) + 2.0 * nbf * nbf * cfg["nocc"]) * cfg["nmat"]
         slice_rows = int(max(8, min(naux, 15.0 * cores * 25e9 / per_row)))
         slice_rows = min(slice_rows, int(4e9 / (8.0 * keep.sum())))  # <= 4 GB host slice
     sp = oracle.Sparsity(keep.astype(np.uint8), slice_rows)
     P = oracle.synth_fill(sp, 0, slice_rows, workloads.SEED, amp)
     Cl = [C] * cfg["nmat"]
-    Crl = None if Cr is None else [Cr] * cfg["nmat"]
-    D = [C @ (C if Cr is None else Cr).T] * cfg["nmat"]
+    D = [C @ (C if Crl is None else Crl[i]).T for i in range(cfg["nmat"])]
     times, parts = [], None
     for it in range(warmup + steps):
         t0 = time.perf_counter()
@@ -134,23 +136,34 @@ def main():
     from psi4_b200 import workloads
 
     cfg = dict(workloads.CONFIGS[args.workload])
+    if args.response:
+        cfg["nmat"] = args.response
     nbf, naux, nocc, nmat = cfg["nbf"], cfg["naux"], cfg["nocc"], cfg["nmat"]
     keep = workloads.pair_mask(nbf, cfg["mask"])
     amp = workloads.amplitude(nbf)
     C = workloads.orbitals(nbf, nocc)
-    Cr = workloads.orbitals(nbf, nocc, workloads.SEED + 1) if args.nonsymmetric else None
+    Cr = workloads.orbitals(nbf, nocc, workloads.SEED + 1) if (args.nonsymmetric or args.response) else None
+    # one (C_left, C_right, D) triple per matrix.  Default: the same pair nmat times, each uploaded and transformed on
+    # its own.  --response: ONE C_left object and a different C_right per right-hand side.
+    Cl = [C] * nmat
+    if args.response:
+        Crl = [workloads.orbitals(nbf, nocc, workloads.SEED + 1 + i) for i in range(nmat)]
+    else:
+        Crl = None if Cr is None else [Cr] * nmat
+    D = [C @ C.T] * nmat if Crl is None else ([C @ Cr.T] * nmat if not args.response else [C @ x.T for x in Crl])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": f"{args.workload}: nbf={nbf} naux={naux} nocc={nocc} nmat={nmat} "
-                          f"kept_pairs={int(keep.sum())} lr_symmetric={Cr is None} do_J=1 do_K=1",
+                          f"kept_pairs={int(keep.sum())} lr_symmetric={Cr is None} do_J=1 do_K=1"
+                          + (f" response: {nmat} right-hand sides share one C_left" if args.response else ""),
               "pair_mask": workloads.mask_info(cfg["mask"]),
-              "q_sharding": f"Q split over {world} rank(s)", "l2": "inputs_exceed_l2 (tensor shard >> 126 MB)"}
+              "q_sharding": f"Q split over {world} rank(s)" + ("; every rank uploads C/D, rank 0 reads J/K" if world > 1 else ""), "l2": "inputs_exceed_l2 (tensor shard >> 126 MB)"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        cb, times = cpu_baseline(cfg, keep, amp, C, Cr, args.cpu_slice, steps=args.steps, warmup=args.warmup)
+        cb, times = cpu_baseline(cfg, keep, amp, C, Crl, args.cpu_slice, steps=args.steps, warmup=args.warmup)
         line = {"metric": METRIC, "value": cb["value"], "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": cb["value"], "higher_is_better": False, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "impl": "reference",
@@ -197,10 +210,8 @@ def main():
         eng = Engine(args.gpus)
         eng.set_layout(nbf, naux, d.small_skips_, d.big_skips_, d.schwarz_fun_index_)
         eng.fill_synthetic(0, workloads.SEED, amp)
-        Cl = [C] * nmat
-        Crl = None if Cr is None else [Cr] * nmat
-        D = [C @ (C if Cr is None else Cr).T] * nmat
-        eng.register_host(D[0])
+        for x in {id(x): x for x in D}.values():
+            eng.register_host(x)
         for _ in range(args.warmup):
             eng.compute(Cl, Crl, D, reuse_outputs=True)
         dev_ms, launches, parts = 0.0, 0, {"ms_j": 0.0, "ms_half": 0.0, "ms_kgemm": 0.0, "ms_allreduce": 0.0}
@@ -228,13 +239,12 @@ def main():
     eng.fill_synthetic(0, workloads.SEED, amp)
     fill_s = time.perf_counter() - t0
 
-    Cl = [C] * nmat
-    Crl = None if Cr is None else [Cr] * nmat
-    D = [C @ (C if Cr is None else Cr).T] * nmat
     n2b = nbf * nbf * 8
-    dC = [eng.dev_put(C) for _ in range(nmat)]
-    dCr = None if Cr is None else [eng.dev_put(Cr) for _ in range(nmat)]
-    dD = [eng.dev_put(D[0]) for _ in range(nmat)]
+    # device operands mirror the host lists: a matrix passed twice is one buffer passed twice only under --response
+    # (the engine recognises a repeated C_left by identity there); otherwise every matrix gets its own copy
+    dC = [eng.dev_put(C)] * nmat if args.response else [eng.dev_put(C) for _ in range(nmat)]
+    dCr = None if Crl is None else [eng.dev_put(x) for x in Crl]
+    dD = [eng.dev_put(x) for x in D]
     dJ = [eng.dev_alloc(n2b) for _ in range(nmat)]
     dK = [eng.dev_alloc(n2b) for _ in range(nmat)]
     noccs = [nocc] * nmat
@@ -272,14 +282,17 @@ def main():
     # ---- end-to-end arm: host pointers through b200jk_compute ----
     # D, J, K live in persistent caller matrices, as psi4's D_ao_/J_ao_/K_ao_ do (allocated once, jk.cc:355-446); the
     # glue page-locks them once (b200jk_register_host).  C is a fresh pageable array every iteration and is staged.
-    eng.register_host(D[0])
+    for x in {id(x): x for x in D}.values():
+        eng.register_host(x)
+    # the SCF driver is one process: rank 0 reads the all-reduced result, the other ranks only contribute to it
+    fetch = rank == 0
     for _ in range(min(args.warmup, 2)):
-        eng.compute(Cl, Crl, D, reuse_outputs=True)
+        eng.compute(Cl, Crl, D, reuse_outputs=True, fetch=fetch)
     barrier()
     w0 = time.perf_counter()
     e2e_parts = {"ms_h2d": 0.0, "ms_d2h": 0.0}
     for _ in range(args.steps):
-        J, K, _ = eng.compute(Cl, Crl, D, reuse_outputs=True)  # persistent J/K matrices, as psi4's JK owns them
+        J, K, _ = eng.compute(Cl, Crl, D, reuse_outputs=True, fetch=fetch)  # persistent J/K, as psi4's JK owns them
         st = eng.stats()
         launches += st["launches"]
         for k in e2e_parts:
@@ -291,7 +304,7 @@ def main():
     # sanity: the two arms agree bit for bit (deterministic reductions)
     Jd = eng.dev_get(dJ[0], (nbf, nbf))
     Kd = eng.dev_get(dK[0], (nbf, nbf))
-    arms_equal = bool(np.array_equal(Jd, J[0]) and np.array_equal(Kd, K[0]))
+    arms_equal = bool(np.array_equal(Jd, J[0]) and np.array_equal(Kd, K[0])) if fetch else True
 
     if rank != 0:
         if world > 1:
@@ -331,7 +344,7 @@ def main():
 
     cb = None
     if world == 1 and not args.no_cpu_baseline:
-        cb, _ = cpu_baseline(cfg, keep, amp, C, Cr, args.cpu_slice)
+        cb, _ = cpu_baseline(cfg, keep, amp, C, Crl, args.cpu_slice)
 
     line = {
         "metric": METRIC, "value": value, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -117,6 +117,12 @@ int b200jk_fit_stats(const b200jk_t* h, double* ms_gemm, double* flops);
  *                   untasked products may be NULL.
  *   wK              requires tensors M1PPQ and WPPQ; symmetrised (A+A^T)/2 when lr_symmetric
  *                   (MemDFJK.cc:104-110).
+ *   repeated C_left When Cr != NULL and Cl[i] is the matrix Cl[i-1] again (same pointer, or same nocc and values) --
+ *                   the reference's response builds push ONE occupied block as every C_left (twoel_Hx,
+ *                   libscf_solver/rhf.cc:466-484) -- the first half transform is kept instead of recomputed
+ *                   (dfhelper.cc:3364 recomputes it); results are bit-identical.  B200JK_NO_T1_REUSE=1 disables it.
+ *   worker ranks    In rank mode a rank other than 0 may pass J = K = wK = NULL: it takes part in the build and the
+ *                   all-reduce and brings nothing home.
  * Host pointers are not retained past the call. */
 int b200jk_compute(b200jk_t* h, int nmat, const double* const* Cl, const double* const* Cr, const int* nocc,
                    const double* const* D, double* const* J, double* const* K, double* const* wK, int do_J,

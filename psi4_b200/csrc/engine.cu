@@ -111,6 +111,8 @@ struct Shard {
     std::vector<cudaEvent_t> evpool;
     size_t evused = 0;
     uint64_t launches = 0;
+    // half transforms skipped in the current build because C_left repeated (Task::same_left): sum of q rows, q rows x nocc
+    double skipped_q = 0, skipped_qo = 0;
 };
 }  // namespace
 
@@ -573,6 +575,11 @@ struct Task {
     int max_o;
     size_t n2;
     int nprod;  // tasked products
+    // same_left[i]: C_left[i] is the matrix C_left[i-1] again (same nocc, same values).  The reference's response
+    // callers pass ONE occupied block as every C_left (twoel_Hx: `Cl.push_back(Co)`, libscf_solver/rhf.cc:466-484,
+    // uhf.cc, TDSCF) and DFHelper re-transforms it for every right-hand side (dfhelper.cc:3364); here the first half
+    // transform is kept and only T2 = transform(C_right[i]) is recomputed.
+    std::vector<char> same_left;
 };
 
 // Grow the per-shard work buffers for this task and pick the Q chunk of the K build.
@@ -675,6 +682,7 @@ int run_device_J(b200jk* h, Shard& s, const Task& t, const double* const* dD) {
 // half transform of each density also produces d_part, the first J sweep (see HalfWsParams).
 int run_device_K(b200jk* h, Shard& s, const Task& t, const double* const* dCl, const double* const* dCr,
                  const double* const* dD, int qc) {
+    s.skipped_q = s.skipped_qo = 0;
     if (!t.do_K && !t.do_wK) return 0;
     CK(cudaSetDevice(s.dev));
     const size_t N = h->nbf, n2 = t.n2;
@@ -689,18 +697,22 @@ int run_device_K(b200jk* h, Shard& s, const Task& t, const double* const* dCl, c
         if (wk ? !t.do_wK : !t.do_K) continue;
         const int tenL = wk ? B200JK_TENSOR_M1PPQ : B200JK_TENSOR_PPQ;
         const int tenR = wk ? B200JK_TENSOR_WPPQ : B200JK_TENSOR_PPQ;
+        int t1_of = -1;  // matrix whose first half transform s.T1 holds in full (single Q chunk only)
         for (int i = 0; i < t.nmat; i++) {
             int o = t.nocc[i];
             if (!o) continue;  // dfhelper.cc:3354-3357
             int op = round_up(o, 2);
             bool one_T = t.lr && !wk;  // T2 = T1 (:3367-3368)
+            // C_left repeated (response right-hand sides): T1 of the previous matrix is this matrix's T1
+            const bool reuse_T1 = !one_T && t.same_left[i] && t1_of == i - 1 && qc >= s.nq;
             {
                 PhaseScope ps(s, 1);
-                if ((rc = run_transpose(h, s, dCl[i], o, s.Ctl, ldc, op))) return rc;
+                if (!reuse_T1 && (rc = run_transpose(h, s, dCl[i], o, s.Ctl, ldc, op))) return rc;
                 if (!one_T && (rc = run_transpose(h, s, t.lr ? dCl[i] : dCr[i], o, s.Ctr, ldc, op))) return rc;
             }
             double* Kout = (wk ? outW : outK) + i * n2;
             FuseJ fj_store, *fj = nullptr;
+            // the density row can ride on either transform of the Ppq tensor: on T1 normally, on T2 when T1 is reused
             if (!wk && t.do_J && dD && dD[i] && can_fuse_j(o)) {
                 const int ldd = round_up((int)N, 2);
                 fj_store.Dm = s.Dm + (size_t)i * N * ldd;
@@ -719,14 +731,21 @@ int run_device_K(b200jk* h, Shard& s, const Task& t, const double* const* dCl, c
                 int nqc = std::min(qc, s.nq - qb);
                 {
                     PhaseScope ps(s, 1);
-                    if ((rc = run_half(h, s, tenL, s.Ctl, ldc, o, op, qb, nqc, s.T1, fj))) return rc;
-                    if (!one_T && (rc = run_half(h, s, tenR, s.Ctr, ldc, o, op, qb, nqc, s.T2))) return rc;
+                    if (reuse_T1) {
+                        s.skipped_q += nqc;
+                        s.skipped_qo += (double)nqc * o;
+                    } else if ((rc = run_half(h, s, tenL, s.Ctl, ldc, o, op, qb, nqc, s.T1, fj))) {
+                        return rc;
+                    }
+                    FuseJ* fj2 = reuse_T1 ? fj : nullptr;
+                    if (!one_T && (rc = run_half(h, s, tenR, s.Ctr, ldc, o, op, qb, nqc, s.T2, fj2))) return rc;
                 }
                 {
                     PhaseScope ps(s, 2);
                     if ((rc = run_kgemm(h, s, s.T1, one_T ? s.T1 : s.T2, nqc * op, one_T, Kout))) return rc;
                 }
             }
+            t1_of = (qc >= s.nq) ? i : -1;
             if (wk && t.lr) {
                 hermitivitize_kernel<<<dim3(((unsigned)N + 127) / 128, (unsigned)N), 128, 0, s.stream>>>(Kout, (int)N);
                 s.launches++;
@@ -764,6 +783,11 @@ void account_work(b200jk* h, const Task& t) {
             st.half_bytes += 2 * (8.0 * Aloc * P + 8.0 * N * Aloc * o);
             st.kgemm_flops += 2.0 * N * N * Aloc * o;
         }
+    }
+    // transforms not executed because C_left repeated are not credited (never count un-executed flops)
+    for (auto& s : h->sh) {
+        st.half_flops -= 2.0 * P * s.skipped_qo;
+        st.half_bytes -= 8.0 * P * s.skipped_q + 8.0 * N * s.skipped_qo;
     }
 }
 
@@ -1233,7 +1257,11 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
     if (nmat == 0) return 0;
     if ((do_K || do_wK) && !Cl) return fail(h, B200JK_ERR_INVALID, "K tasked without C_left");
     if (do_J && !D) return fail(h, B200JK_ERR_INVALID, "J tasked without D");
-    if ((do_J && !J) || (do_K && !K) || (do_wK && !wK)) return fail(h, B200JK_ERR_INVALID, "tasked output array is NULL");
+    // rank mode: a rank other than 0 may pass no output arrays at all -- it takes part in the build and the all-reduce
+    // but brings nothing home (one host process needs the result once; psi4 is a single process)
+    const bool fetch = !(host_ops && h->rank_mode && h->rank != 0 && !J && !K && !wK);
+    if (fetch && ((do_J && !J) || (do_K && !K) || (do_wK && !wK)))
+        return fail(h, B200JK_ERR_INVALID, "tasked output array is NULL");
 
     Task t;
     t.nmat = nmat;
@@ -1248,6 +1276,15 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
     for (int i = 0; i < nmat; i++) t.max_o = std::max(t.max_o, nocc[i]);
     if (t.nprod == 0) return 0;
     const size_t N = h->nbf, n2 = t.n2;
+    t.same_left.assign(nmat, 0);
+    if ((do_K || do_wK) && !t.lr && !getenv("B200JK_NO_T1_REUSE"))
+        for (int i = 1; i < nmat; i++) {
+            if (!nocc[i] || nocc[i] != nocc[i - 1]) continue;
+            // device operands: identity only; host operands: identity or equal contents (USO2AO makes per-matrix
+            // AO copies of one SO block, jk.cc:404-446)
+            t.same_left[i] = Cl[i] == Cl[i - 1] ||
+                             (host_ops && memcmp(Cl[i], Cl[i - 1], N * (size_t)nocc[i] * sizeof(double)) == 0);
+        }
     begin_compute(h);
 
     std::vector<int> qc(h->sh.size());
@@ -1394,7 +1431,7 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
         }
         if ((rc = allreduce(h, ol.offK, ol.countKW, true))) return rc;
         CK(cudaSetDevice(s0.dev));
-        if (ol.countKW) {
+        if (ol.countKW && fetch) {
             Phase ph;
             ph.tag = 5;
             ph.a = get_event(s0);
@@ -1415,7 +1452,7 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
         CK(cudaEventRecord(evKhome, s0.copy));
         if ((rc = allreduce(h, ol.offJ, ol.countJ, false))) return rc;
         CK(cudaSetDevice(s0.dev));
-        if (ol.countJ) {
+        if (ol.countJ && fetch) {
             PhaseScope ps(s0, 5);
             for (int i = 0; i < nmat; i++) {
                 size_t off = ol.offJ + (size_t)i * n2;
@@ -1447,7 +1484,7 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
         CK(cudaEventRecord(total[i].b, s.stream));
         s.phases.push_back(total[i]);
     }
-    if (host_ops) {
+    if (host_ops && fetch) {
         // K / wK leave the staging buffer while the GPU is still busy with J
         CK(cudaSetDevice(s0.dev));
         CK(cudaEventSynchronize(evKhome));
@@ -1463,7 +1500,7 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
         CK(cudaStreamSynchronize(s.stream));
         CK(cudaStreamSynchronize(s.copy));
     }
-    if (host_ops && do_J)
+    if (host_ops && do_J && fetch)
         for (int i = 0; i < nmat; i++)
             if (!is_pinned(h, J[i], n2 * 8)) par_memcpy(J[i], h->pin_out + ol.offJ + (size_t)i * n2, n2 * 8);
     account_work(h, t);

@@ -214,13 +214,14 @@ class Engine:
     def unregister_host(self, arr: np.ndarray):
         self._check(self.L.b200jk_unregister_host(self.h, ct.c_void_p(arr.ctypes.data)))
 
-    def compute(self, Cl, Cr, D, do_J=True, do_K=True, do_wK=False, reuse_outputs=False):
+    def compute(self, Cl, Cr, D, do_J=True, do_K=True, do_wK=False, reuse_outputs=False, fetch=True):
         """Host-operand build.  Cl/Cr: lists of (nbf, nocc_i) arrays (Cr None => lr_symmetric);
         D: list of (nbf,nbf).  Returns (J, K, wK) lists (None where untasked).
 
         reuse_outputs: write into persistent per-engine result matrices, as psi4's JK does (J_/K_ are allocated
         once in JK::allocate_JK, jk.cc:355-389, and overwritten by every compute(); callers re-fetch J()[i],
-        jk.h:149-159).  Otherwise fresh arrays are returned."""
+        jk.h:149-159).  Otherwise fresh arrays are returned.
+        fetch=False (rank mode, rank != 0 only): take part in the build and the all-reduce, bring nothing home."""
         n = self.nbf
         nmat = len(Cl) if Cl is not None else len(D)
         if not n:
@@ -229,9 +230,9 @@ class Engine:
         Cr_ = None if Cr is None else [np.ascontiguousarray(c, dtype=np.float64).reshape(n, -1) for c in Cr]
         D_ = None if D is None else [np.ascontiguousarray(d, dtype=np.float64).reshape(n, n) for d in D]
         nocc = (ct.c_int * nmat)(*([c.shape[1] for c in Cl_] if Cl_ is not None else [0] * nmat))
-        J = self._outputs("J", nmat, reuse_outputs) if do_J else None
-        K = self._outputs("K", nmat, reuse_outputs) if do_K else None
-        wK = self._outputs("wK", nmat, reuse_outputs) if do_wK else None
+        J = self._outputs("J", nmat, reuse_outputs) if do_J and fetch else None
+        K = self._outputs("K", nmat, reuse_outputs) if do_K and fetch else None
+        wK = self._outputs("wK", nmat, reuse_outputs) if do_wK and fetch else None
         rc = self.L.b200jk_compute(self.h, nmat, _ptr_array(Cl_), _ptr_array(Cr_), nocc, _ptr_array(D_),
                                    _ptr_array(J), _ptr_array(K), _ptr_array(wK), int(do_J), int(do_K), int(do_wK))
         self._check(rc)

@@ -82,6 +82,13 @@ err = max(max(np.abs(J[i] - Jo[i]).max(), np.abs(K[i] - Ko[i]).max()) for i in r
 st = e.stats()
 print(f"RANK{rank} err={err:.3e} q=[{st['q_begin']},{st['q_end']}) allreduce_ms={st['ms_allreduce']:.3f}", flush=True)
 assert err < 1e-10
+# worker ranks may bring nothing home (b200jk_compute with NULL outputs on rank != 0): rank 0's result is unchanged
+J2, K2, _ = e.compute(Cl, Cr, [x @ y.T for x, y in zip(Cl, Cr)], fetch=(rank == 0))
+if rank == 0:
+    assert all(np.array_equal(a, b) for a, b in zip(J + K, J2 + K2))
+else:
+    assert J2 is None and K2 is None
+print(f"RANK{rank} fetch_ok", flush=True)
 dist.barrier(); dist.destroy_process_group()
 """
 
@@ -98,6 +105,7 @@ def test_one_process_per_gpu_torchrun(tmp_path):
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "RANK0 err=" in r.stdout and "RANK1 err=" in r.stdout
+    assert "RANK0 fetch_ok" in r.stdout and "RANK1 fetch_ok" in r.stdout
 
 
 LEGACY_SCRIPT = r"""

@@ -352,3 +352,55 @@ def test_registered_host_buffers_same_result(oracle):
     assert J2[0] is J1[0] and np.array_equal(J2[0], 4 * J0[0]) and np.array_equal(K2[0], 4 * K0[0])
     e.unregister_host(D)
     e.close()
+
+
+@pytest.mark.parametrize("do_wK", [False, True])
+def test_response_batch_shared_c_left(oracle, monkeypatch, do_wK):
+    """The reference's response callers (twoel_Hx: `Cl.push_back(Co)` for every trial vector, libscf_solver/rhf.cc:466-484)
+    hand ONE occupied block as every C_left and a different C_right per vector.  The engine keeps the first half
+    transform across such matrices; the result must be the oracle's and bit-identical to the build that recomputes it,
+    and the skipped transforms must not be credited as work."""
+    from psi4_b200 import Engine
+
+    rng = np.random.default_rng(909 + do_wK)
+    n, a, o = 70, 64, 9
+    keep = random_mask(rng, n, 0.6)
+    sp, d, B, P = make(oracle, rng, n, a, keep, 0.2)
+    Co = rng.standard_normal((n, o))
+    # [shared object, shared object, equal copy (USO2AO-style), a different left block, shared with THAT one, other nocc]
+    other = rng.standard_normal((n, o))
+    Cl = [Co, Co, Co.copy(), other, other, rng.standard_normal((n, o + 2))]
+    Cr = [rng.standard_normal(c.shape) for c in Cl]
+    D = [x @ y.T for x, y in zip(Cl, Cr)]
+    e = Engine(1)
+    e.set_layout(n, a, d.small_skips_, d.big_skips_, d.schwarz_fun_index_)
+    e.upload(0, P)
+    kw = {}
+    if do_wK:
+        M1, W = sym_tensor(rng, a, n, 0.2), sym_tensor(rng, a, n, 0.2)
+        P1, PW = d.pack(M1), d.pack(W)
+        e.upload(1, P1)
+        e.upload(2, PW)
+        kw = dict(do_wK=True, m1Ppq=P1, wPpq=PW)
+    J, K, wK = e.compute(Cl, Cr, D, do_wK=do_wK)
+    st = e.stats()
+    Jo, Ko, wKo, _ = oracle.build_JK(sp, P, Cl, Cr, D=D, **kw)
+    check(J, Jo, what="J")
+    check(K, Ko, what="K")
+    if do_wK:
+        check(wK, wKo, what="wK")
+    monkeypatch.setenv("B200JK_NO_T1_REUSE", "1")
+    J2, K2, wK2 = e.compute(Cl, Cr, D, do_wK=do_wK)
+    st2 = e.stats()
+    for x, y in zip(J + K + (wK if do_wK else []), J2 + K2 + (wK2 if do_wK else [])):
+        assert np.array_equal(x, y)
+    # 12 transforms (24 with wK) without reuse; matrices 1, 2 and 4 skip their first one
+    ntr, skipped = (24, 6) if do_wK else (12, 3)
+    assert st2["half_flops"] > 0
+    # nocc differs for the last matrix, so compare through the per-transform unit 2*A*P*o
+    unit = 2.0 * a * int(d.small_skips_[n])
+    per_pass = 2 * unit * (5 * o + (o + 2))
+    assert st2["half_flops"] == pytest.approx(per_pass * (2 if do_wK else 1), rel=1e-12)
+    assert st["half_flops"] == pytest.approx(st2["half_flops"] - skipped * unit * o, rel=1e-12)
+    assert ntr * 2 > skipped
+    e.close()
