@@ -131,8 +131,22 @@ def cpu_baseline(cfg, keep, amp, C, Crl, slice_rows, steps=1, warmup=0):
             "blas": oracle.lib().oracle_blas_config().decode()}, times
 
 
+_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    print(json.dumps(line), file=_OUT or sys.stdout, flush=True)
+
+
 def main():
+    global _OUT
     args = parse()
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner under NCCL_DEBUG,
+    # OpenBLAS notices) is sent to stderr by pointing fd 1 at fd 2 and keeping a private copy of the real stdout
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     from psi4_b200 import workloads
 
     cfg = dict(workloads.CONFIGS[args.workload])
@@ -170,7 +184,7 @@ def main():
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -225,13 +239,13 @@ def main():
                 parts[k] += st[k] / args.steps
         e2e_ms = (time.perf_counter() - w0) * 1e3 / args.steps
         n2b = nbf * nbf * 8
-        print(json.dumps({
+        emit({
             "metric": METRIC, "value": dev_ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": dict(config, q_sharding=f"Q split over {args.gpus} GPUs driven by ONE process"),
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(args.gpus * nmat * (C.nbytes + n2b)),
                     "d2h_bytes_per_step": int(nmat * 2 * n2b)},
-            "gpu_launches": int(launches), "kernels_ms_max_over_gpus": parts, "mode": "single_process"}))
+            "gpu_launches": int(launches), "kernels_ms_max_over_gpus": parts, "mode": "single_process"})
         return
     eng = Engine(rank=rank, world=world, device=local_rank, nccl_id=nccl_id)
     eng.set_layout(nbf, naux, d.small_skips_, d.big_skips_, d.schwarz_fun_index_)
@@ -356,7 +370,7 @@ def main():
         "wall_ms_per_step": wall_ms, "arms_bit_identical": arms_equal,
         "hbm": {"tensor_gb": st_dev["hbm_tensor_bytes"] / 1e9, "work_gb": st_dev["hbm_work_bytes"] / 1e9, "fill_s": fill_s},
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
