@@ -92,8 +92,15 @@ struct Shard {
     double* Dm = nullptr;        // [nmat][nbf][ldd] density operands of the fused first J sweep
     size_t dm_cap = 0;
     std::vector<char> fused;     // per density of the current build: first J sweep done inside the half transform
-    double *fit_raw = nullptr, *fit_t = nullptr;
-    size_t fit_raw_cap = 0, fit_t_cap = 0;
+    // unfitted integrals of a group, double-buffered so the H2D of the next group (copy stream) runs under the
+    // kernels of the current one; fit_raw_free[b]: the kernels that read buffer b have finished
+    double *fit_raw[2] = {nullptr, nullptr}, *fit_t = nullptr;
+    size_t fit_raw_cap[2] = {0, 0}, fit_t_cap = 0;
+    cudaEvent_t fit_raw_free[2] = {nullptr, nullptr};
+    unsigned fit_next = 0;
+    char* fit_meta[2] = {nullptr, nullptr};  // page-locked index tables of a group (see fit_group)
+    size_t fit_meta_cap[2] = {0, 0};
+    cudaEvent_t fit_meta_done[2] = {nullptr, nullptr};
     size_t* d_fit_dst_off = nullptr;
     size_t* d_fit_src_off = nullptr;
     int *d_fit_dst_ld = nullptr, *d_fit_mi = nullptr, *d_fit_j0 = nullptr, *d_fit_m = nullptr;
@@ -137,6 +144,20 @@ struct b200jk {
     std::string err;
     b200jk_stats stats;
     std::vector<std::pair<const char*, size_t>> pinned;  // caller ranges registered with b200jk_register_host
+    // page-locked staging ring of the tensor producers (b200jk_upload_rows / b200jk_fit_rows): the caller's block is
+    // copied here by a few threads and the call returns; the DMA and the kernels run behind it
+    struct StageSlot {
+        double* buf = nullptr;
+        size_t cap = 0;                 // doubles
+        std::vector<cudaEvent_t> done;  // per shard: the last DMA out of this slot
+    } stage[2];
+    unsigned stage_next = 0;
+    struct FitTiming {
+        int shard;
+        cudaEvent_t a, b;
+        double flops;
+    };
+    std::vector<FitTiming> fit_pending;  // metric-GEMM event pairs not yet read back
 };
 
 namespace {
@@ -843,7 +864,7 @@ void par_memcpy(void* dst, const void* src, size_t bytes) {
         memcpy(dst, src, bytes);
         return;
     }
-    int nt = (int)std::min<size_t>(4, bytes / chunk);
+    int nt = (int)std::min<size_t>(bytes >= ((size_t)64 << 20) ? 8 : 4, bytes / chunk);
     std::vector<std::thread> th;
     size_t per = (bytes / nt + 63) & ~(size_t)63;
     for (int i = 1; i < nt; i++) {
@@ -852,6 +873,48 @@ void par_memcpy(void* dst, const void* src, size_t bytes) {
     }
     memcpy(dst, src, std::min(per, bytes));
     for (auto& x : th) x.join();
+}
+
+// Next slot of the staging ring, free (every DMA issued out of it has finished) and at least `doubles` large.
+int stage_acquire(b200jk* h, size_t doubles, b200jk::StageSlot** out) {
+    b200jk::StageSlot& sl = h->stage[h->stage_next++ & 1];
+    if (sl.done.size() != h->sh.size()) sl.done.assign(h->sh.size(), nullptr);
+    for (size_t si = 0; si < h->sh.size(); si++) {
+        CK(cudaSetDevice(h->sh[si].dev));
+        if (!sl.done[si])
+            CK(cudaEventCreateWithFlags(&sl.done[si], cudaEventDisableTiming));
+        else
+            CK(cudaEventSynchronize(sl.done[si]));
+    }
+    if (doubles > sl.cap) {
+        if (sl.buf) CK(cudaFreeHost(sl.buf));
+        sl.buf = nullptr;
+        sl.cap = 0;
+        CK(cudaHostAlloc((void**)&sl.buf, doubles * sizeof(double), cudaHostAllocPortable));
+        sl.cap = doubles;
+    }
+    *out = &sl;
+    return 0;
+}
+
+// Group size of the tensor producers; B200JK_STAGE_BYTES overrides it (tests drive many groups through the ring).
+size_t stage_budget(size_t dflt) {
+    const char* e = getenv("B200JK_STAGE_BYTES");
+    if (e && *e) {
+        unsigned long long v = strtoull(e, nullptr, 10);
+        if (v) return (size_t)v;
+    }
+    return dflt;
+}
+
+// Everything the tensor producers queued has finished (streams of every shard drained).
+int producers_sync(b200jk* h) {
+    for (auto& s : h->sh) {
+        CK(cudaSetDevice(s.dev));
+        CK(cudaStreamSynchronize(s.copy));
+        CK(cudaStreamSynchronize(s.stream));
+    }
+    return 0;
 }
 
 int check_compute_args(b200jk* h, int nmat, const int* nocc, bool do_J, bool do_K, bool do_wK) {
@@ -899,13 +962,19 @@ void free_shard(Shard& s) {
         if (s.tensor[w]) cudaFree(s.tensor[w]);
         if (s.d_amaps[w]) cudaFree(s.d_amaps[w]);
     }
-    void* ptrs[] = {s.d_counter, s.d_tiles_sym, s.d_tiles_full, s.d_mpos, s.d_metric, s.fit_raw, s.fit_t, s.Dm,
+    void* ptrs[] = {s.d_counter, s.d_tiles_sym, s.d_tiles_full, s.d_mpos, s.d_metric, s.fit_raw[0], s.fit_raw[1], s.fit_t, s.Dm,
                     s.d_fit_dst_off, s.d_fit_src_off, s.d_fit_dst_ld, s.d_fit_mi, s.d_fit_j0, s.d_fit_m,
                     s.d_row_off, s.d_ldm, s.d_sp, s.d_ign, s.d_cols, s.d_cols_off, s.in, s.out,
                     s.Ctl,       s.Ctr,   s.dpart, s.T1,  s.T2,     s.ws};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto e : s.evpool) cudaEventDestroy(e);
+    for (auto e : s.fit_raw_free)
+        if (e) cudaEventDestroy(e);
+    for (auto e : s.fit_meta_done)
+        if (e) cudaEventDestroy(e);
+    for (auto p : s.fit_meta)
+        if (p) cudaFreeHost(p);
     if (s.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s.comm);
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.copy) cudaStreamDestroy(s.copy);
@@ -1023,7 +1092,16 @@ int b200jk_unregister_host(b200jk_t* h, void* ptr) {
 void b200jk_destroy(b200jk_t* h) {
     if (!h) return;
     for (auto& r : h->pinned) cudaHostUnregister((void*)r.first);
+    for (auto& f : h->fit_pending) {
+        cudaEventDestroy(f.a);
+        cudaEventDestroy(f.b);
+    }
     for (auto& s : h->sh) free_shard(s);
+    for (auto& sl : h->stage) {
+        for (auto e : sl.done)
+            if (e) cudaEventDestroy(e);
+        if (sl.buf) cudaFreeHost(sl.buf);
+    }
     if (h->pin_in) cudaFreeHost(h->pin_in);
     if (h->pin_out) cudaFreeHost(h->pin_out);
     delete h;
@@ -1140,25 +1218,71 @@ int b200jk_upload_rows(b200jk_t* h, int which, size_t m0, size_t m1, const doubl
     if (which < 0 || which > 2 || m0 > m1 || m1 > h->nbf || !host_rows) return fail(h, B200JK_ERR_INVALID, "bad upload args");
     int rc = alloc_tensor(h, which);
     if (rc) return rc;
-    const size_t A = h->naux;
-    for (auto& s : h->sh) {
-        if (!s.nq) continue;
-        CK(cudaSetDevice(s.dev));
-        for (size_t m = m0; m < m1; m++) {
-            size_t sp = h->sp[m];
-            const double* src = host_rows + (h->big_skips[m] - h->big_skips[m0]) + (size_t)s.q0 * sp;
-            double* dst = s.tensor[which] + h->row_off_unit[m] * (size_t)s.nq;
-            CK(cudaMemcpy2DAsync(dst, (size_t)h->ldm[m] * 8, src, sp * 8, sp * 8, (size_t)s.nq, cudaMemcpyHostToDevice,
-                                 s.stream));
+    // Q range the local shards hold (everything for an in-process handle, one shard's rows in rank mode): only that
+    // part of each row-block is touched
+    size_t qlo = h->naux, qhi = 0;
+    for (auto& s : h->sh)
+        if (s.nq) {
+            qlo = std::min<size_t>(qlo, s.q0);
+            qhi = std::max<size_t>(qhi, s.q1);
         }
-        (void)A;
+    const size_t total_bytes = (h->big_skips[m1] - h->big_skips[m0]) * sizeof(double);
+    const bool direct = is_pinned(h, host_rows, total_bytes);  // page-locked by the caller: DMA straight out of it
+    // Pageable source: groups of row-blocks (<= 256 MB of the local Q range) go through the page-locked ring -- a few
+    // threads fill one slot while the DMA engines drain the other; the call returns when the last slot is filled.
+    const size_t budget = stage_budget((size_t)256 << 20);
+    size_t ma = m0;
+    while (ma < m1 && qlo < qhi) {
+        size_t mb = ma, doubles = 0;
+        while (mb < m1) {
+            size_t add = (qhi - qlo) * (size_t)h->sp[mb];
+            if (mb > ma && (doubles + add) * 8 > budget) break;
+            doubles += add;
+            mb++;
+        }
+        b200jk::StageSlot* slot = nullptr;
+        std::vector<size_t> soff(mb - ma, 0);
+        if (!direct) {
+            if ((rc = stage_acquire(h, doubles, &slot))) return rc;
+            // the local Q range of each row-block is one contiguous slab of the caller's block
+            size_t off = 0;
+            std::vector<std::thread> th;
+            const int nt = 8;
+            for (size_t m = ma; m < mb; m++) {
+                soff[m - ma] = off;
+                off += (qhi - qlo) * (size_t)h->sp[m];
+            }
+            for (int t = 0; t < nt; t++)
+                th.emplace_back([&, t] {
+                    for (size_t m = ma + t; m < mb; m += nt) {
+                        size_t sp = h->sp[m];
+                        memcpy(slot->buf + soff[m - ma], host_rows + (h->big_skips[m] - h->big_skips[m0]) + qlo * sp,
+                               (qhi - qlo) * sp * sizeof(double));
+                    }
+                });
+            for (auto& x : th) x.join();
+        }
+        for (size_t si = 0; si < h->sh.size(); si++) {
+            Shard& s = h->sh[si];
+            if (!s.nq) continue;
+            CK(cudaSetDevice(s.dev));
+            for (size_t m = ma; m < mb; m++) {
+                size_t sp = h->sp[m];
+                const double* src = direct ? host_rows + (h->big_skips[m] - h->big_skips[m0]) + (size_t)s.q0 * sp
+                                           : slot->buf + soff[m - ma] + ((size_t)s.q0 - qlo) * sp;
+                double* dst = s.tensor[which] + h->row_off_unit[m] * (size_t)s.nq;
+                CK(cudaMemcpy2DAsync(dst, (size_t)h->ldm[m] * 8, src, sp * 8, sp * 8, (size_t)s.nq, cudaMemcpyHostToDevice,
+                                     s.stream));
+            }
+            if (slot) CK(cudaEventRecord(slot->done[si], s.stream));
+        }
+        ma = mb;
     }
-    for (auto& s : h->sh) {
-        CK(cudaSetDevice(s.dev));
-        CK(cudaStreamSynchronize(s.stream));
-    }
-    if (m0 == 0 && m1 == h->nbf) h->uploaded[which] = true;
-    if (m1 == h->nbf) h->uploaded[which] = true;  // streaming: last block completes the tensor
+    // the caller's own memory must stay untouched until the DMA has read it; staged data is already ours.  The last
+    // block of the tensor drains everything so "uploaded" means resident.
+    if (direct || m1 == h->nbf)
+        if ((rc = producers_sync(h))) return rc;
+    if (m1 == h->nbf) h->uploaded[which] = true;  // streaming: the last block completes the tensor
     h->stats.hbm_tensor_bytes = 0;
     for (int w = 0; w < 3; w++)
         if (h->sh[0].tensor[w]) h->stats.hbm_tensor_bytes += h->sh[0].tensor_doubles * 8;
@@ -1208,6 +1332,7 @@ int b200jk_download_rows(b200jk_t* h, int which, size_t m, size_t q0, size_t q1,
         if (a >= b || !s.tensor[which]) continue;
         any = true;
         CK(cudaSetDevice(s.dev));
+        CK(cudaStreamSynchronize(s.stream));  // uploads / fitting kernels queued behind an earlier call
         const double* src = s.tensor[which] + h->row_off_unit[m] * (size_t)s.nq + (a - s.q0) * (size_t)h->ldm[m];
         CK(cudaMemcpy2D(host_out + (a - q0) * sp, sp * 8, src, (size_t)h->ldm[m] * 8, sp * 8, b - a, cudaMemcpyDeviceToHost));
     }

@@ -91,3 +91,54 @@ def test_gpu_tu1_energy_with_device_fitting():
     jk.initialize()
     E = scf.RHF(mol, P, jk).compute_energy()
     assert abs(E - a["scf_total_energy"]) < 1e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("registered", [False, True])
+def test_gpu_producers_pipeline_with_reused_block_buffer(oracle, monkeypatch, registered):
+    """psi4 fills ONE block buffer over and over (Mp / Ppq rows, dfhelper.cc:553-585).  b200jk_fit_rows and
+    b200jk_upload_rows return before the GPU is done with a block, so the buffer may be overwritten right away: a
+    pageable buffer is copied into the page-locked ring first, a registered one is held until its DMA has finished.
+    A tiny group size drives many groups through both ring slots and both device buffers."""
+    from psi4_b200 import Engine
+
+    monkeypatch.setenv("B200JK_STAGE_BYTES", str(48 * 1024))
+    rng = np.random.default_rng(77)
+    n, a, block = 120, 97, 17
+    keep, d, U, met = case(rng, n, a, 0.7)
+    sp = oracle.Sparsity(keep.astype(np.uint8), a)
+    ref = oracle.contract_metric_AO_core_symm(sp, d.pack_symm(U), met)
+    e = Engine(1)
+    e.set_layout(n, a, d.small_skips_, d.big_skips_, d.schwarz_fun_index_)
+    e.set_metric(met)
+    biggest = max(int(d.symm_big_skips_[min(n, m0 + block)] - d.symm_big_skips_[m0]) for m0 in range(0, n, block))
+    buf = np.zeros(biggest)
+    if registered:
+        e.register_host(buf)
+    for m0 in range(0, n, block):
+        m1 = min(n, m0 + block)
+        blk = d.pack_symm(U, m0, m1)
+        buf[:blk.size] = blk
+        e.fit_rows(0, m0, m1, buf)
+        buf[:] = np.nan  # the caller reuses its buffer immediately
+    for m in range(n):
+        got = e.download_rows(0, m, 0, a).ravel()
+        want = ref[int(d.big_skips_[m]):int(d.big_skips_[m + 1])]
+        assert np.abs(got - want).max() < 1e-12 * max(1.0, np.abs(ref).max()), f"row-block {m}"
+    # the same for the fitted-rows upload (streaming b200jk_upload_rows into tensor slot 1)
+    biggest = max(int(d.big_skips_[min(n, m0 + block)] - d.big_skips_[m0]) for m0 in range(0, n, block))
+    buf2 = np.zeros(biggest)
+    if registered:
+        e.register_host(buf2)
+    for m0 in range(0, n, block):
+        m1 = min(n, m0 + block)
+        rows = ref[int(d.big_skips_[m0]):int(d.big_skips_[m1])]
+        buf2[:rows.size] = rows
+        e.upload_rows(1, m0, m1, buf2[:rows.size])
+        buf2[:] = np.nan
+    for m in range(n):
+        assert np.array_equal(e.download_rows(1, m, 0, a).ravel(), ref[int(d.big_skips_[m]):int(d.big_skips_[m + 1])])
+    if registered:
+        e.unregister_host(buf)
+        e.unregister_host(buf2)
+    e.close()

@@ -19,6 +19,7 @@ ap.add_argument("--nbf", type=int, default=600)
 ap.add_argument("--naux", type=int, default=4740)
 ap.add_argument("--block", type=int, default=40)
 ap.add_argument("--pageable", action="store_true", help="do not page-lock the block buffer")
+ap.add_argument("--gpus", type=int, default=1, help="Q shards driven by this one process")
 args = ap.parse_args()
 n, a = args.nbf, args.naux
 d = DFHelper(n, a)
@@ -26,10 +27,11 @@ d.prepare_sparsity(keep=np.ones((n, n), bool))
 rng = np.random.default_rng(0)
 g = rng.standard_normal((a, a))
 met = g @ g.T / a + np.eye(a)
-e = Engine(1)
+e = Engine(args.gpus)
 e.set_layout(n, a, d.small_skips_, d.big_skips_, d.schwarz_fun_index_)
 e.set_metric(met)
 wall = 0.0
+calls = []
 first_block = None
 # psi4 reuses ONE block buffer (Qpq / Mp, dfhelper.cc:553) for every p-block: page-lock it once (b200jk_register_host)
 # so the raw integrals go up by DMA at PCIe speed; --pageable shows the unregistered path
@@ -46,10 +48,13 @@ for m0 in range(0, n, args.block):
         first_block = (m0, m1, blk.copy())
     t0 = time.perf_counter()
     e.fit_rows(0, m0, m1, blk)
-    wall += time.perf_counter() - t0
+    calls.append(time.perf_counter() - t0)
+    wall += calls[-1]
 st = e.fit_stats()
 out = {"nbf": n, "naux": a, "pair_columns": int(d.symm_big_skips_[n] // a), "raw_gb": float(d.symm_big_skips_[n]) * 8 / 1e9,
-       "gpu_gemm_ms": st["ms_gemm"], "gpu_gemm_tflops": st["tflops"], "gpu_wall_s_incl_h2d": wall,
+       "gpu_gemm_ms": st["ms_gemm"], "gpu_gemm_tflops": st["tflops"], "gpu_wall_s_incl_h2d": wall, "gpus": args.gpus,
+       # fit_rows returns once the caller's block has been read; only the last call waits for the GPU to finish
+       "host_blocked_s_before_last_block": sum(calls[:-1]), "last_call_s": calls[-1],
        "block_buffer": "pageable" if args.pageable else "registered (page-locked once)"}
 try:
     import dfjk_oracle as oracle
