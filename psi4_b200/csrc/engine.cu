@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <string>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -152,6 +153,7 @@ struct b200jk {
         std::vector<cudaEvent_t> done;  // per shard: the last DMA out of this slot
     } stage[2];
     unsigned stage_next = 0;
+    double stage_wait_s = 0, stage_alloc_s = 0, stage_copy_s = 0;  // host time of the producers (B200JK_STAGE_TRACE)
     struct FitTiming {
         int shard;
         cudaEvent_t a, b;
@@ -875,10 +877,25 @@ void par_memcpy(void* dst, const void* src, size_t bytes) {
     for (auto& x : th) x.join();
 }
 
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// B200JK_STAGE_TRACE=1: one stderr line per producer call with where the host time went
+bool stage_trace() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("B200JK_STAGE_TRACE");
+        on = (e && e[0] == '1') ? 1 : 0;
+    }
+    return on == 1;
+}
+
 // Next slot of the staging ring, free (every DMA issued out of it has finished) and at least `doubles` large.
-int stage_acquire(b200jk* h, size_t doubles, b200jk::StageSlot** out) {
+// Page-locking host memory is slow (measured 2.2 GB/s for cudaHostAlloc on the B200 box), so a slot is allocated
+// once at the producers' group size (`reserve`) and only ever grows for a single row-block larger than that.
+int stage_acquire(b200jk* h, size_t doubles, size_t reserve, b200jk::StageSlot** out) {
     b200jk::StageSlot& sl = h->stage[h->stage_next++ & 1];
     if (sl.done.size() != h->sh.size()) sl.done.assign(h->sh.size(), nullptr);
+    double t0 = now_s();
     for (size_t si = 0; si < h->sh.size(); si++) {
         CK(cudaSetDevice(h->sh[si].dev));
         if (!sl.done[si])
@@ -886,12 +903,16 @@ int stage_acquire(b200jk* h, size_t doubles, b200jk::StageSlot** out) {
         else
             CK(cudaEventSynchronize(sl.done[si]));
     }
+    h->stage_wait_s += now_s() - t0;
     if (doubles > sl.cap) {
+        t0 = now_s();
         if (sl.buf) CK(cudaFreeHost(sl.buf));
         sl.buf = nullptr;
         sl.cap = 0;
-        CK(cudaHostAlloc((void**)&sl.buf, doubles * sizeof(double), cudaHostAllocPortable));
-        sl.cap = doubles;
+        const size_t want = std::max(doubles, reserve);
+        CK(cudaHostAlloc((void**)&sl.buf, want * sizeof(double), cudaHostAllocPortable));
+        sl.cap = want;
+        h->stage_alloc_s += now_s() - t0;
     }
     *out = &sl;
     return 0;
@@ -1216,6 +1237,8 @@ int b200jk_upload_rows(b200jk_t* h, int which, size_t m0, size_t m1, const doubl
     if (!h) return B200JK_ERR_INVALID;
     if (!h->have_layout) return fail(h, B200JK_ERR_INVALID, "upload before set_layout");
     if (which < 0 || which > 2 || m0 > m1 || m1 > h->nbf || !host_rows) return fail(h, B200JK_ERR_INVALID, "bad upload args");
+    const double t_call = now_s();
+    h->stage_wait_s = h->stage_alloc_s = h->stage_copy_s = 0;
     int rc = alloc_tensor(h, which);
     if (rc) return rc;
     // Q range the local shards hold (everything for an in-process handle, one shard's rows in rank mode): only that
@@ -1243,7 +1266,8 @@ int b200jk_upload_rows(b200jk_t* h, int which, size_t m0, size_t m1, const doubl
         b200jk::StageSlot* slot = nullptr;
         std::vector<size_t> soff(mb - ma, 0);
         if (!direct) {
-            if ((rc = stage_acquire(h, doubles, &slot))) return rc;
+            if ((rc = stage_acquire(h, doubles, std::min<size_t>(budget / 8, h->big_skips[h->nbf]), &slot))) return rc;
+            const double tc = now_s();
             // the local Q range of each row-block is one contiguous slab of the caller's block
             size_t off = 0;
             std::vector<std::thread> th;
@@ -1261,6 +1285,7 @@ int b200jk_upload_rows(b200jk_t* h, int which, size_t m0, size_t m1, const doubl
                     }
                 });
             for (auto& x : th) x.join();
+            h->stage_copy_s += now_s() - tc;
         }
         for (size_t si = 0; si < h->sh.size(); si++) {
             Shard& s = h->sh[si];
@@ -1280,8 +1305,13 @@ int b200jk_upload_rows(b200jk_t* h, int which, size_t m0, size_t m1, const doubl
     }
     // the caller's own memory must stay untouched until the DMA has read it; staged data is already ours.  The last
     // block of the tensor drains everything so "uploaded" means resident.
+    const double ts = now_s();
     if (direct || m1 == h->nbf)
         if ((rc = producers_sync(h))) return rc;
+    if (stage_trace())
+        fprintf(stderr, "[b200jk] upload_rows [%zu,%zu) %.1f MB %s: total %.4f s (ring wait %.4f, pin alloc %.4f, copy %.4f, drain %.4f)\n",
+                m0, m1, total_bytes / 1e6, direct ? "direct" : "staged", now_s() - t_call, h->stage_wait_s, h->stage_alloc_s,
+                h->stage_copy_s, now_s() - ts);
     if (m1 == h->nbf) h->uploaded[which] = true;  // streaming: the last block completes the tensor
     h->stats.hbm_tensor_bytes = 0;
     for (int w = 0; w < 3; w++)

@@ -209,6 +209,8 @@ extern "C" int b200jk_fit_rows(b200jk_t* h, int which, size_t m0, size_t m1, con
     if (!h->have_layout) return fail(h, B200JK_ERR_INVALID, "fit_rows before set_layout");
     if (which < 0 || which > 2 || m0 > m1 || m1 > h->nbf || !host_sym) return fail(h, B200JK_ERR_INVALID, "bad fit_rows args");
     const bool with_metric = h->sh[0].have_metric;
+    const double t_call = now_s();
+    h->stage_wait_s = h->stage_alloc_s = h->stage_copy_s = 0;
     int rc = alloc_tensor(h, which);
     if (rc) return rc;
     if (m0 == 0) {
@@ -216,11 +218,11 @@ extern "C" int b200jk_fit_rows(b200jk_t* h, int which, size_t m0, size_t m1, con
         h->ms_fit_gemm = h->fit_flops = 0;
     }
     const size_t A = h->naux;
-    // Groups of row-blocks of <= 512 MB of raw integrals.  Every local shard needs the whole group (the contraction
+    // Groups of row-blocks of <= 256 MB of raw integrals.  Every local shard needs the whole group (the contraction
     // runs over all of the auxiliary index), so a pageable block is staged ONCE in the page-locked ring and DMA'd to
     // all shards concurrently; the call returns as soon as the caller's block has been read -- psi4 computes the next
     // block of integrals (dfhelper.cc:566-585) while the GPUs transpose, contract and mirror this one.
-    const size_t budget = stage_budget((size_t)512 << 20);
+    const size_t budget = stage_budget((size_t)256 << 20);
     const size_t total_bytes = (h->symm_big_skips[m1] - h->symm_big_skips[m0]) * sizeof(double);
     const bool direct = is_pinned(h, host_sym, total_bytes);
     std::vector<std::pair<int, cudaEvent_t>> h2d;  // direct mode: copies that still read the caller's block
@@ -236,8 +238,12 @@ extern "C" int b200jk_fit_rows(b200jk_t* h, int which, size_t m0, size_t m1, con
         const double* src = host_sym + (h->symm_big_skips[ma] - h->symm_big_skips[m0]);
         b200jk::StageSlot* slot = nullptr;
         if (!direct) {
-            if ((rc = stage_acquire(h, std::max<size_t>(bytes / 8, 1), &slot))) return rc;
+            if ((rc = stage_acquire(h, std::max<size_t>(bytes / 8, 1), std::min<size_t>(budget / 8, h->symm_big_skips[h->nbf]),
+                                    &slot)))
+                return rc;
+            const double tc = now_s();
             par_memcpy(slot->buf, src, bytes);
+            h->stage_copy_s += now_s() - tc;
             src = slot->buf;
         }
         for (size_t si = 0; si < h->sh.size(); si++) {
@@ -254,11 +260,16 @@ extern "C" int b200jk_fit_rows(b200jk_t* h, int which, size_t m0, size_t m1, con
         }
         ma = mb;
     }
+    const double ts = now_s();
     for (auto& e : h2d) {
         CK(cudaSetDevice(e.first));
         CK(cudaEventSynchronize(e.second));
         CK(cudaEventDestroy(e.second));
     }
+    if (stage_trace())
+        fprintf(stderr, "[b200jk] fit_rows [%zu,%zu) %.1f MB %s: queued in %.4f s (ring wait %.4f, pin alloc %.4f, copy %.4f, h2d wait %.4f)\n",
+                m0, m1, total_bytes / 1e6, direct ? "direct" : "staged", now_s() - t_call, h->stage_wait_s, h->stage_alloc_s,
+                h->stage_copy_s, now_s() - ts);
     if (m1 == h->nbf) {
         // the last block completes the tensor: drain the pipeline so "uploaded" means resident and fitted
         if ((rc = producers_sync(h))) return rc;
