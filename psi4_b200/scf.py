@@ -294,3 +294,70 @@ class UHF:
             Cb = np.ascontiguousarray(diag(Fb)[:, : self.nb])
         self.energy = E
         return E
+
+
+class ROHF:
+    """Restricted open-shell SCF on a JK object, the call pattern of ROHF::form_G (libscf_solver/rohf.cc:935-966): ONE
+    jk.compute() over C_left = [C_docc, C_socc] (two matrices with different column counts, C_right empty), then
+    Ga = 2 J[0] + J[1] - (K[0] + K[1]),  Gb = 2 J[0] + J[1] - K[0].  Orbitals from the Guest-Saunders effective Fock
+    matrix in the MO basis (rohf.cc:330-400: closed-open block Fb, open-virtual block Fa, average elsewhere);
+    E = Enuc + 1/2 [ (Da+Db).H + Da.Fa + Db.Fb ]."""
+
+    def __init__(self, mol: Molecule, primary: BasisSet, jk, multiplicity=3, e_convergence=1e-10, d_convergence=1e-8,
+                 maxiter=200):
+        self.mol, self.primary, self.jk = mol, primary, jk
+        self.e_conv, self.d_conv, self.maxiter = e_convergence, d_convergence, maxiter
+        mints = getattr(jk, "mints_", None) or MintsHelper(mol, primary)
+        self.S, T, V = mints.one_electron()
+        self.H = T + V
+        self.Enuc = mol.nuclear_repulsion()
+        ne = mol.nelectron()
+        self.na = (ne + multiplicity - 1) // 2
+        self.nb = ne - self.na
+        self.X = matrix_power(self.S, -0.5, 1e-10)
+        self.iterations = []
+
+    def compute_energy(self) -> float:
+        X, S, H, jk, nb, na = self.X, self.S, self.H, self.jk, self.nb, self.na
+        _, C2 = np.linalg.eigh(X @ H @ X)  # core guess
+        C = X @ C2
+        diis = _DIIS()
+        Eold = 0.0
+        for it in range(self.maxiter):
+            Cd, Cs = np.ascontiguousarray(C[:, :nb]), np.ascontiguousarray(C[:, nb:na])
+            jk.C_clear()
+            jk.C_left_add(Cd)
+            jk.C_left_add(Cs)
+            jk.compute()
+            J, K = jk.J(), jk.K()
+            G = 2.0 * J[0] + J[1]
+            Fa, Fb = H + G - (K[0] + K[1]), H + G - K[0]
+            Dc, Do = Cd @ Cd.T, Cs @ Cs.T
+            Da, Db = Dc + Do, Dc
+            E = self.Enuc + 0.5 * float(np.sum((Da + Db) * H) + np.sum(Da * Fa) + np.sum(Db * Fb))
+            # effective Fock matrix in the current MO basis
+            fa, fb = C.T @ Fa @ C, C.T @ Fb @ C
+            feff = 0.5 * (fa + fb)
+            feff[:nb, nb:na] = fb[:nb, nb:na]
+            feff[nb:na, :nb] = fb[nb:na, :nb]
+            feff[nb:na, na:] = fa[nb:na, na:]
+            feff[na:, nb:na] = fa[na:, nb:na]
+            # orbital gradient: the occupied-virtual type blocks (closed-open, closed-virtual, open-virtual)
+            g = np.zeros_like(feff)
+            g[:nb, nb:] = feff[:nb, nb:]
+            g[nb:na, na:] = feff[nb:na, na:]
+            g = g - g.T
+            drms = float(np.sqrt(np.mean(g ** 2)))
+            self.iterations.append((E, E - Eold, drms))
+            if abs(E - Eold) < self.e_conv and drms < self.d_conv:
+                break
+            Eold = E
+            # DIIS on the effective Fock matrix expressed in the fixed orthogonal AO basis (C^-1 = C^T S)
+            Ci = C.T @ S
+            F_ao, g_ao = Ci.T @ feff @ Ci, Ci.T @ g @ Ci
+            diis.add(X @ F_ao @ X, X @ g_ao @ X)
+            Fx = diis.extrapolate() if it >= 1 else X @ F_ao @ X
+            _, C2 = np.linalg.eigh(Fx)
+            C = X @ C2
+        self.energy, self.C = E, C
+        return E

@@ -61,6 +61,7 @@ anchors = {
         "nuclear_repulsion": grab("scf5/input.dat", r'"Nuclear"\s*:\s*(\d+\.\d+)'),
         "singlet_rhf_df": grab("scf5/input.dat", r'"Singlet": \{\s*"Canonical" : -?\d+\.\d+, #TEST\s*"DF"\s*: (-\d+\.\d+)'),
         "triplet_uhf_df": grab("scf5/input.dat", r'"Triplet UHF": \{\s*"Canonical" : -?\d+\.\d+, #TEST\s*"DF"\s*: (-\d+\.\d+)'),
+        "triplet_rohf_df": grab("scf5/input.dat", r'"Triplet ROHF": \{\s*"Canonical" : -?\d+\.\d+, #TEST\s*"DF"\s*: (-\d+\.\d+)'),
         "tolerance_decimals": 6,
     },
     "dlpnocc4_decane_def2svp": {
