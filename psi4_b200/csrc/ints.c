@@ -149,6 +149,13 @@ static sh_t unit_shell(sh_t at) { /* s "function" == 1 on the same centre: turns
     return r;
 }
 
+/* Range separation: omega > 0 switches the operator from 1/r12 to erf(omega r12)/r12 (IntegralFactory::erf_eri,
+ * used for wPpq_ in DFHelper::prepare_AO_wK_core, lib3index/dfhelper.cc:589-699).  For two Gaussian charge
+ * distributions with reduced exponent alpha this is the Coulomb formula with alpha_w = alpha w^2 / (alpha + w^2) in the
+ * Hermite integrals and an extra factor sqrt(alpha_w / alpha).  Set by the *_erf entry points before their parallel
+ * region and reset after it. */
+static double g_omega = 0.0;
+
 /* ---- contracted cartesian shell quartet (ab|cd) -> out[na][nb][nc][nd] -------------------------- */
 #define MAXC NCART(LMAX)
 static void eri_quartet(sh_t A, sh_t B, sh_t C, sh_t D, double* out, double* work /* >= (LTOT+2)*RD^3 + RD^3 */) {
@@ -179,8 +186,13 @@ static void eri_quartet(sh_t A, sh_t B, sh_t C, sh_t D, double* out, double* wor
                     hermite_E(C.l, D.l, c, d, C.y, D.y, E2y);
                     hermite_E(C.l, D.l, c, d, C.z, D.z, E2z);
                     double alpha = p * q / (p + q);
-                    hermite_R(L, alpha, Px - Qx, Py - Qy, Pz - Qz, R0, Rw);
                     double pref = 2.0 * pow(M_PI, 2.5) / (p * q * sqrt(p + q)) * cab * C.c[ic] * D.c[id];
+                    if (g_omega > 0.0) {
+                        double aw = alpha * g_omega * g_omega / (alpha + g_omega * g_omega);
+                        pref *= sqrt(aw / alpha);
+                        alpha = aw;
+                    }
+                    hermite_R(L, alpha, Px - Qx, Py - Qy, Pz - Qz, R0, Rw);
                     for (int kc = 0; kc < nc; kc++)
                         for (int kd = 0; kd < nd; kd++) {
                             int lx = cc[kc][0] + cd[kd][0], ly = cc[kc][1] + cd[kd][1], lz = cc[kc][2] + cd[kd][2];
@@ -395,6 +407,21 @@ int ints_three_center(int nsa, const double* axyz, const int* al, const int* anp
     return 0;
 }
 
+/* (A|erf(omega r)/r|mn), same layout (the unfitted wPpq_ integrals, dfhelper.cc:683-692) */
+int ints_three_center_erf(int nsa, const double* axyz, const int* al, const int* anp, const int* apo, const double* ae,
+                          const double* ac, int nsp, const double* pxyz, const int* pl, const int* pnp, const int* ppo,
+                          const double* pe, const double* pc, double omega, double* out) {
+    if (!(omega > 0.0)) return 2;
+    g_omega = omega;
+    int rc = ints_three_center(nsa, axyz, al, anp, apo, ae, ac, nsp, pxyz, pl, pnp, ppo, pe, pc, out);
+    g_omega = 0.0;
+    return rc;
+}
+
+/* general erf-attenuated (ab|cd) block (tests) */
+int ints_quartet_erf(const double* xyz4, const int* l4, const int* np4, const double* const* e4, const double* const* c4,
+                     double omega, double* out);
+
 /* (MU NU | MU NU) cartesian block of one shell pair: out[nm][nn][nm][nn] */
 int ints_pair_diagonal(int ns, const double* xyz, const int* l, const int* np, const int* po, const double* e,
                        const double* c, int MU, int NU, double* out) {
@@ -420,4 +447,13 @@ int ints_quartet(const double* xyz4, const int* l4, const int* np4, const double
     eri_quartet(s[0], s[1], s[2], s[3], out, work);
     free(work);
     return 0;
+}
+
+int ints_quartet_erf(const double* xyz4, const int* l4, const int* np4, const double* const* e4, const double* const* c4,
+                     double omega, double* out) {
+    if (!(omega > 0.0)) return 2;
+    g_omega = omega;
+    int rc = ints_quartet(xyz4, l4, np4, e4, c4, out);
+    g_omega = 0.0;
+    return rc;
 }

@@ -173,6 +173,7 @@ class BasisSet:
         if puream is not None:
             spherical = puream
         bs = BasisSet(name, [], spherical)
+        bs.mol = mol
         for ia, sym in enumerate(mol.symbols):
             for l, e, c in table[sym.upper()]:
                 bs.shells.append(Shell(l, np.array(e), np.array(c), mol.xyz[ia].copy(), ia))
@@ -214,6 +215,9 @@ class BasisSet:
 
     def nbf(self) -> int:
         return self._nbf
+
+    def molecule(self) -> "Molecule":
+        return self.mol
 
     def nshell(self) -> int:
         return len(self.shells)
@@ -262,11 +266,16 @@ class MintsHelper:
             raise RuntimeError("ints_two_center failed")
         return aux.U @ out @ aux.U.T
 
-    def three_center(self, aux: BasisSet) -> np.ndarray:
-        """(A|mn) as a dense (naux, nbf, nbf) array, dfhelper.cc:1284-1347."""
+    def three_center(self, aux: BasisSet, omega: float = 0.0) -> np.ndarray:
+        """(A|mn) as a dense (naux, nbf, nbf) array, dfhelper.cc:1284-1347; omega > 0: (A|erf(omega r)/r|mn), the
+        integrals of IntegralFactory::erf_eri that fill wPpq_ (dfhelper.cc:596, :683-692)."""
         P = self.primary
         out = np.zeros((aux.ncart, P.ncart, P.ncart))
-        rc = _ints().ints_three_center(*aux._args(), *P._args(), out.ctypes.data_as(ct.POINTER(ct.c_double)))
+        if omega > 0.0:
+            rc = _ints().ints_three_center_erf(*aux._args(), *P._args(), ct.c_double(omega),
+                                               out.ctypes.data_as(ct.POINTER(ct.c_double)))
+        else:
+            rc = _ints().ints_three_center(*aux._args(), *P._args(), out.ctypes.data_as(ct.POINTER(ct.c_double)))
         if rc:
             raise RuntimeError("ints_three_center failed")
         t = np.einsum("Aa,amn->Amn", aux.U, out, optimize=True)

@@ -96,6 +96,24 @@ class JK:
 
     def initialize(self): self.preiterations()
     def finalize(self): self.postiterations()
+    def basisset(self): return getattr(self, "primary_", None)  # jk.h:417
+
+    def computed_shells_per_iter(self, n_let: str | None = None):
+        """jk.cc:239-246.  Only the integral-direct algorithms tally shell n-lets (DirectJK.cc:955-957,
+        CompositeJK.cc:320-338); MemDFJK never fills the map, so it is empty here as well."""
+        tally = self.__dict__.setdefault("computed_shells_per_iter_", {})
+        return tally if n_let is None else tally[n_let]
+
+    @staticmethod
+    def build_JK(primary, auxiliary, do_wK: bool = False, doubles: int = 0, **options):
+        """JK::build_JK with SCF_TYPE=MEM_DF (jk.cc:143-150, export_fock.cc:50-57): a MemDFJK over the B200 engine
+        for psi4_b200 basis sets (integrals.BasisSet).  options: cutoff, condition, ngpu, omega, fit_on_device."""
+        from . import scf
+
+        jk = scf.build_jk(primary.molecule(), primary, auxiliary, do_wK=do_wK, **options)
+        if doubles:
+            jk.set_memory(doubles)
+        return jk
 
     def compute(self):
         """JK::compute, jk.cc:595-681 (C1 branch: no USO2AO/AO2USO work when nirrep == 1)."""

@@ -40,9 +40,11 @@ class DFTensors:
     """Host part of DFHelper::initialize for the in-core STORE method (dfhelper.cc:149-215, :514-588)."""
 
     def __init__(self, mol: Molecule, primary: BasisSet, aux: BasisSet, cutoff: float = 1e-12, condition: float = 1e-10,
-                 do_wK: bool = False, fit_on_device: bool = False):
-        if do_wK:
-            raise NotImplementedError("range-separated (erf-attenuated) integrals are not in the host front end yet")
+                 do_wK: bool = False, fit_on_device: bool = False, omega: float = 0.0):
+        if do_wK and not omega > 0.0:
+            raise ValueError("do_wK needs omega > 0 (JK::set_omega)")
+        if do_wK and fit_on_device:
+            raise NotImplementedError("wK tensors are fitted on the host in this driver")
         mints = MintsHelper(mol, primary)
         self.mints = mints
         self.dfh = DFHelper(primary.nbf(), aux.nbf())
@@ -52,7 +54,12 @@ class DFTensors:
         metric = mints.metric(aux)                                                 # prepare_metric :1462-1476
         self.Jm12 = matrix_power(metric, -0.5, condition)                          # compute_metric :1491-1517
         Amn = mints.three_center(aux)                                              # :1284-1347
-        self.Ppq = self.dense = self.unfitted_sym = None
+        self.Ppq = self.dense = self.unfitted_sym = self.m1Ppq = self.wPpq = None
+        if do_wK:
+            # prepare_AO_wK_core :589-699 -- m1Ppq_ = J^-1 (A|mn) (wmpower_ = -1.0), wPpq_ = (A|erf(omega r)/r|mn) unfitted
+            self.dfh.set_do_wK(True)
+            self.m1Ppq = self.dfh.pack(np.tensordot(matrix_power(metric, -1.0, condition), Amn, axes=([1], [0])))
+            self.wPpq = self.dfh.pack(mints.three_center(aux, omega))
         if fit_on_device:
             # hand the unfitted n >= m half to the engine (b200jk_fit_rows); metric contraction + mirror run on the GPU
             self.unfitted_sym = self.dfh.pack_symm(Amn)
@@ -64,19 +71,25 @@ class DFTensors:
 
 
 def build_jk(mol: Molecule, primary: BasisSet, aux: BasisSet, *, cutoff: float = 1e-12, condition: float = 1e-10,
-             ngpu: int = 1, jk_factory=None, fit_on_device: bool = False, fit_block: int = 64):
+             ngpu: int = 1, jk_factory=None, fit_on_device: bool = False, fit_block: int = 64, do_wK: bool = False,
+             omega: float = 0.0):
     """JK::build_JK analogue.  jk_factory(dfh, Ppq) may construct another JK implementation (tests).
     fit_on_device: the engine contracts the metric itself (b200jk_set_metric / b200jk_fit_rows), fed in blocks of
     fit_block basis functions like the p-blocked loop of prepare_AO_core."""
-    t = DFTensors(mol, primary, aux, cutoff, condition, fit_on_device=fit_on_device)
+    t = DFTensors(mol, primary, aux, cutoff, condition, fit_on_device=fit_on_device, do_wK=do_wK, omega=omega)
     if fit_on_device:
         jk = MemDFJK(t.dfh, ngpu=ngpu, unfitted=(t.unfitted_sym, t.Jm12, fit_block))
+    elif do_wK:
+        jk = (jk_factory or (lambda dfh, Ppq, m1, w: MemDFJK(dfh, Ppq, m1, w, ngpu=ngpu)))(t.dfh, t.Ppq, t.m1Ppq, t.wPpq)
+        jk.set_do_wK(True)
+        jk.set_omega(omega)
     else:
         jk = (jk_factory or (lambda dfh, Ppq: MemDFJK(dfh, Ppq, ngpu=ngpu)))(t.dfh, t.Ppq)
     jk.set_cutoff(cutoff)
     if hasattr(jk, "set_condition"):
         jk.set_condition(condition)
     jk.mints_ = t.mints
+    jk.primary_ = primary
     return jk
 
 
