@@ -26,6 +26,11 @@ __device__ __forceinline__ void cp_async16(double* smem, const double* gmem, int
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
 }
+// 16-byte copy through L1 (the gathered C^T rows are re-read by every item of a row-block); src_bytes < 16 zero-fills
+__device__ __forceinline__ void cp_async16_ca(double* smem, const double* gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async8(double* smem, const double* gmem, int src_bytes) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");

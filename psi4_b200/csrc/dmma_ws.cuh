@@ -298,8 +298,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         reg_dealloc_producer();
         if (tid == 0) prefetch_tmap(&ctmap);
         uint32_t g = 0;  // global stage counter
-        const int kk = tid & 15;
-        const int chunk = kk >> 1, half = kk & 1;
         int slot = 0;
         int w = sm.sched[0];
         while (w < p.nitems) {
@@ -342,7 +340,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
                 const int irows = min(p.o, i0 + BN) - i0;  // valid C^T rows of this tile
                 const int* cols = p.cols + p.cols_off[m];
                 const double* drow = p.Dm + (size_t)m * p.ldd;
-                int col_next = (kk < K) ? __ldg(cols + kk) : -1;
+                // Each thread owns one PAIR of k positions (2*pj, 2*pj+1) of the stage = one 16-byte chunk of every
+                // tile row.  Kept partners come in runs (the functions of an atom), so most pairs are two adjacent,
+                // 16-byte-aligned columns of C^T and go with ONE 16-byte cp.async; the others with two 8-byte ones.
+                const int pj = tid & 7;
+                int c0n = (2 * pj < K) ? __ldg(cols + 2 * pj) : -1;
+                int c1n = (2 * pj + 1 < K) ? __ldg(cols + 2 * pj + 1) : -1;
                 for (int kt = 0; kt < nkt; kt++, g++) {
                     const int s = g % WS_STAGES;
                     const uint32_t ph = (g / WS_STAGES) & 1;
@@ -352,18 +355,33 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
                         mbar_arrive_expect_tx(&sm.full[s], WS_A_STAGE);
                         tma_load_2d(sm.As + s * WS_A_STAGE, amap, kt * BK, p.qbeg + qt * BM, &sm.full[s]);
                     }
-                    const int col = col_next;
-                    const int kn = (kt + 1) * BK + kk;
-                    col_next = (kt + 1 < nkt && kn < K) ? __ldg(cols + kn) : -1;
+                    const int c0 = c0n, c1 = c1n;
+                    const int kn = (kt + 1) * BK + 2 * pj;
+                    c0n = (kt + 1 < nkt && kn < K) ? __ldg(cols + kn) : -1;
+                    c1n = (kt + 1 < nkt && kn + 1 < K) ? __ldg(cols + kn + 1) : -1;
                     uint8_t* bs = sm.Bs + s * B_STAGE;
-#pragma unroll 4
-                    for (int r = tid >> 4; r < BN; r += WS_PRODUCER_THREADS / 16) {
-                        const bool drow_here = fused && r == p.rd;
-                        int bytes = (col >= 0 && (r < irows || drow_here)) ? 8 : 0;
-                        const double* src = !bytes ? p.Ct : (drow_here ? drow + col : p.Ct + (size_t)(i0 + r) * p.ldc + col);
-                        double* dst =
-                            reinterpret_cast<double*>(bs + r * WS_ROW_BYTES + ((chunk ^ (r & 7)) << 4) + (half << 3));
-                        cp_async8(dst, src, bytes);
+                    if (c0 < 0 || (!(c0 & 1) && (c1 == c0 + 1 || c1 < 0))) {
+                        const int nb = c0 < 0 ? 0 : (c1 < 0 ? 8 : 16);  // the rest of the chunk is zero-filled
+#pragma unroll 3
+                        for (int r = tid >> 3; r < BN; r += WS_PRODUCER_THREADS / 8) {
+                            const bool drow_here = fused && r == p.rd;
+                            const int bytes = (r < irows || drow_here) ? nb : 0;
+                            const double* src =
+                                !bytes ? p.Ct : (drow_here ? drow + c0 : p.Ct + (size_t)(i0 + r) * p.ldc + c0);
+                            double* dst = reinterpret_cast<double*>(bs + r * WS_ROW_BYTES + ((pj ^ (r & 7)) << 4));
+                            cp_async16_ca(dst, src, bytes);
+                        }
+                    } else {
+#pragma unroll 3
+                        for (int r = tid >> 3; r < BN; r += WS_PRODUCER_THREADS / 8) {
+                            const bool drow_here = fused && r == p.rd;
+                            const bool live = r < irows || drow_here;
+                            const double* base = drow_here ? drow : p.Ct + (size_t)(i0 + r) * p.ldc;
+                            double* dst = reinterpret_cast<double*>(bs + r * WS_ROW_BYTES + ((pj ^ (r & 7)) << 4));
+                            cp_async8(dst, live ? base + c0 : p.Ct, live ? 8 : 0);  // c0 >= 0 here
+                            const bool l1 = live && c1 >= 0;
+                            cp_async8(dst + 1, l1 ? base + c1 : p.Ct, l1 ? 8 : 0);
+                        }
                     }
                     cp_async_mbar_arrive_noinc(&sm.full[s]);
                 }
