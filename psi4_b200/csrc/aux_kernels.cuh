@@ -21,6 +21,36 @@ __global__ void transpose_c_kernel(const double* __restrict__ C, int nbf, int o,
     }
 }
 
+// Packed copy of the C^T operand of the half transform, one block per row-block m in the tensor's own column order:
+// Cg[m][r][k] = Ct[r][n_k(m)] for r < o, and row r == o holds the density row Dm[m][n_k(m)] of the fused first J sweep
+// (zeros when Dm == nullptr).  Same pitch ld(m) as the tensor, so K3 can fetch both operands of a screened row-block
+// by TMA (through a per-m map with dims {sp(m), o+1}) instead of gathering C^T through the LSU for every work item.
+// grid = (nbf, ceil((o+1)/8)); block 256.
+__global__ void __launch_bounds__(256) gather_ct_kernel(const double* __restrict__ Ct, int ldc, int o,
+                                                         const double* __restrict__ Dm, int ldd,
+                                                         const int* __restrict__ sp, const int* __restrict__ ldm,
+                                                         const size_t* __restrict__ row_off_unit,
+                                                         const int* __restrict__ cols, const size_t* __restrict__ cols_off,
+                                                         double* __restrict__ Cg) {
+    const int m = blockIdx.x;
+    const int K = sp[m], ld = ldm[m];
+    const int R = o + 1;
+    const int* c = cols + cols_off[m];
+    double* out = Cg + row_off_unit[m] * (size_t)R;
+    const int r0 = blockIdx.y * 8;
+    for (int k = threadIdx.x; k < ld; k += 256) {
+        const int col = k < K ? __ldg(c + k) : -1;
+#pragma unroll
+        for (int dr = 0; dr < 8; dr++) {
+            const int r = r0 + dr;
+            if (r >= R) break;
+            double v = 0.0;
+            if (col >= 0) v = r < o ? Ct[(size_t)r * ldc + col] : (Dm ? Dm[(size_t)m * ldd + col] : 0.0);
+            out[(size_t)r * ld + k] = v;
+        }
+    }
+}
+
 // wK post-step of MemDFJK::compute_JK (libfock/MemDFJK.cc:104-110): A <- (A + A^T)/2.
 __global__ void hermitivitize_kernel(double* __restrict__ A, int n) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;

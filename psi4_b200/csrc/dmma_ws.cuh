@@ -271,6 +271,9 @@ struct HalfWsParams {
     int ldd;
     double* dpart;              // [nbf][dstride]
     int dstride;
+    // Pre-gathered C^T (gather_ct_kernel): per-row-block maps {sp(m), o+1} over the packed copy, box 16 x 16*NB.  When
+    // set, screened row-blocks take the all-TMA path too (the density row is row o of the packed block, i.e. tile row rd).
+    const CUtensorMap* cgmaps;
 };
 
 template <int NB>
@@ -332,6 +335,22 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
                             tma_load_2d(sm.Bs + s * B_STAGE, &ctmap_last, kt * BK, i0, &sm.full[s]);
                             tma_load_2d(sm.Bs + s * B_STAGE + p.rd * WS_ROW_BYTES, &dmap, kt * BK, m, &sm.full[s]);
                         }
+                        mbar_arrive_n(&sm.full[s], WS_PRODUCER_THREADS);
+                    }
+                }
+                g += nkt;
+            } else if (p.cgmaps) {
+                // screened row-block, C^T pre-gathered into the tensor's column order: both operands by TMA
+                if (tid == 0) {
+                    const CUtensorMap* cmap = p.cgmaps + m;
+                    for (int kt = 0; kt < nkt; kt++) {
+                        const uint32_t gg = g + kt;
+                        const int s = gg % WS_STAGES;
+                        mbar_wait_backoff(&sm.empty[s], ((gg / WS_STAGES) & 1) ^ 1);
+                        if (kt == 0) sm.meta[s] = w;
+                        mbar_arrive_expect_tx(&sm.full[s], WS_A_STAGE + B_STAGE);
+                        tma_load_2d(sm.As + s * WS_A_STAGE, amap, kt * BK, p.qbeg + qt * BM, &sm.full[s]);
+                        tma_load_2d(sm.Bs + s * B_STAGE, cmap, kt * BK, i0, &sm.full[s]);
                         mbar_arrive_n(&sm.full[s], WS_PRODUCER_THREADS);
                     }
                 }

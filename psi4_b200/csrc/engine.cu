@@ -99,6 +99,14 @@ struct Shard {
     size_t fit_raw_cap[2] = {0, 0}, fit_t_cap = 0;
     cudaEvent_t fit_raw_free[2] = {nullptr, nullptr};
     unsigned fit_next = 0;
+    // pre-gathered C^T of the half transform (gather_ct_kernel) and its per-row-block TMA maps, cached on
+    // (buffer, rows, box rows): in an SCF nocc never changes, so the maps are encoded once
+    double* Cg = nullptr;
+    size_t cg_cap = 0;
+    CUtensorMap* d_cgmaps = nullptr;
+    const double* cg_key_ptr = nullptr;
+    int cg_key_rows = 0, cg_key_box = 0;
+    bool screened = false;  // some row-block keeps fewer than nbf partners
     char* fit_meta[2] = {nullptr, nullptr};  // page-locked index tables of a group (see fit_group)
     size_t fit_meta_cap[2] = {0, 0};
     cudaEvent_t fit_meta_done[2] = {nullptr, nullptr};
@@ -108,6 +116,7 @@ struct Shard {
     size_t fit_cols_cap = 0, fit_nm_cap = 0;
     size_t tensor_doubles = 0;
     size_t* d_row_off = nullptr;
+    size_t* d_row_off_unit = nullptr;  // the same per Q row (sum of ld up to m): layout of the pre-gathered C^T
     int *d_ldm = nullptr, *d_sp = nullptr, *d_ign = nullptr, *d_cols = nullptr;
     size_t* d_cols_off = nullptr;
     // work buffers (grown on demand, kept across calls: SURVEY.md Appendix B "allocate once per handle")
@@ -360,10 +369,49 @@ bool can_fuse_j(int o) {
     return o - (nit - 1) * iw < 16 * NB;
 }
 
+// Pre-gather C^T for the screened row-blocks (all-TMA K3)?  The packed copy costs one pass of 8*P*(o+1) bytes per
+// transform, independent of how many Q rows the shard holds, and buys back the LSU gather (about 3.5 % of K3):
+// worth it from ~1500 Q rows per GPU.  B200JK_CGATHER=1 / 0 forces it on / off.
+bool want_cgather(const Shard& s, int qc) {
+    static int mode = -2;
+    if (mode == -2) {
+        const char* e = getenv("B200JK_CGATHER");
+        mode = !e || !*e ? -1 : (e[0] == '1' ? 1 : 0);
+    }
+    if (use_legacy() || !s.screened) return false;
+    return mode == 1 || (mode == -1 && qc >= 1500);
+}
+
 int run_half_ws(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o, int op, int qbeg, int qc, double* T,
                 const FuseJ* fj) {
     int nit, iw, NB;
     half_tiling(o, op, &nit, &iw, &NB);
+    const CUtensorMap* cgmaps = nullptr;
+    if (want_cgather(s, qc)) {
+        const int R = o + 1;
+        const size_t unit = h->row_off_unit[h->nbf];  // sum of ld(m)
+        int rc = grow(h, &s.Cg, &s.cg_cap, unit * (size_t)R);
+        if (rc) return rc;
+        gather_ct_kernel<<<dim3((unsigned)h->nbf, (unsigned)((R + 7) / 8)), 256, 0, s.stream>>>(
+            Ct, ldc, o, fj ? fj->Dm : nullptr, fj ? fj->ldd : 0, s.d_sp, s.d_ldm, s.d_row_off_unit, s.d_cols, s.d_cols_off, s.Cg);
+        s.launches++;
+        CK(cudaGetLastError());
+        if (!s.d_cgmaps || s.cg_key_ptr != s.Cg || s.cg_key_rows != R || s.cg_key_box != 16 * NB) {
+            std::vector<CUtensorMap> maps(h->nbf);
+            for (size_t m = 0; m < h->nbf; m++)
+                if ((rc = make_map(h, &maps[m], s.Cg + h->row_off_unit[m] * (size_t)R, (uint64_t)h->sp[m], (uint64_t)R,
+                                   (uint64_t)h->ldm[m] * 8, (uint32_t)(16 * NB))))
+                    return rc;
+            if (!s.d_cgmaps) CK(cudaMalloc((void**)&s.d_cgmaps, h->nbf * sizeof(CUtensorMap)));
+            // (pageable source: the copy is staged before the call returns, and it is stream-ordered before K3)
+            CK(cudaMemcpyAsync(s.d_cgmaps, maps.data(), h->nbf * sizeof(CUtensorMap), cudaMemcpyHostToDevice, s.stream));
+            CK(cudaStreamSynchronize(s.stream));
+            s.cg_key_ptr = s.Cg;
+            s.cg_key_rows = R;
+            s.cg_key_box = 16 * NB;
+        }
+        cgmaps = s.d_cgmaps;
+    }
     CUtensorMap ctmap, ctmap_last, dmap;
     int rc = make_map(h, &ctmap, Ct, h->nbf, (uint64_t)o, (uint64_t)ldc * 8, (uint32_t)(16 * NB));
     if (rc) return rc;
@@ -381,6 +429,7 @@ int run_half_ws(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o
     p.ldd = fj ? fj->ldd : 0;
     p.dpart = fj ? fj->dpart : nullptr;
     p.dstride = fj ? fj->dstride : 0;
+    p.cgmaps = cgmaps;
     p.amaps = s.d_amaps[which];
     p.sp = s.d_sp;
     p.cols = s.d_cols;
@@ -632,6 +681,8 @@ int ensure_work(b200jk* h, Shard& s, const Task& t, int* qc_out) {
             CK(cudaMalloc((void**)&s.Ctr, ct * sizeof(double)));
             s.ct_cap = ct;
         }
+        // the pre-gathered C^T (see want_cgather) is claimed before the T buffers size themselves from what is left
+        if (want_cgather(s, s.nq) && (rc = grow(h, &s.Cg, &s.cg_cap, h->row_off_unit[N] * (size_t)(t.max_o + 1)))) return rc;
         bool two = !t.lr || t.do_wK;
         size_t per_q = N * (size_t)op;  // doubles of T per q row
         int qc = s.nq;
@@ -983,7 +1034,7 @@ void free_shard(Shard& s) {
         if (s.tensor[w]) cudaFree(s.tensor[w]);
         if (s.d_amaps[w]) cudaFree(s.d_amaps[w]);
     }
-    void* ptrs[] = {s.d_counter, s.d_tiles_sym, s.d_tiles_full, s.d_mpos, s.d_metric, s.fit_raw[0], s.fit_raw[1], s.fit_t, s.Dm,
+    void* ptrs[] = {s.Cg, s.d_cgmaps, s.d_row_off_unit, s.d_counter, s.d_tiles_sym, s.d_tiles_full, s.d_mpos, s.d_metric, s.fit_raw[0], s.fit_raw[1], s.fit_t, s.Dm,
                     s.d_fit_dst_off, s.d_fit_src_off, s.d_fit_dst_ld, s.d_fit_mi, s.d_fit_j0, s.d_fit_m,
                     s.d_row_off, s.d_ldm, s.d_sp, s.d_ign, s.d_cols, s.d_cols_off, s.in, s.out,
                     s.Ctl,       s.Ctr,   s.dpart, s.T1,  s.T2,     s.ws};
@@ -1203,6 +1254,8 @@ int b200jk_set_layout(b200jk_t* h, size_t nbf, size_t naux, const size_t* small_
         CK(cudaSetDevice(s.dev));
         int rc;
         if ((rc = upload_vec(h, &s.d_row_off, row_off))) return rc;
+        if ((rc = upload_vec(h, &s.d_row_off_unit, h->row_off_unit))) return rc;
+        s.screened = h->small_skips[nbf] < nbf * nbf;
         if ((rc = upload_vec(h, &s.d_ldm, h->ldm))) return rc;
         if ((rc = upload_vec(h, &s.d_sp, h->sp))) return rc;
         if ((rc = upload_vec(h, &s.d_ign, h->ign))) return rc;
@@ -1392,6 +1445,7 @@ int b200jk_hbm_estimate(const b200jk_t* h, size_t max_nocc, int do_wK, uint64_t*
     b += (uint64_t)h->nbf * s.nq * op * 8 * 2;          // T1, T2 (full shard)
     b += (uint64_t)h->nbf * s.nq * 8;                   // dpart
     b += (uint64_t)6 * h->nbf * h->nbf * 8 + ((uint64_t)1 << 30);  // in/out + split-K partials
+    if (want_cgather(s, s.nq)) b += (uint64_t)h->row_off_unit[h->nbf] * (max_nocc + 1) * 8;  // pre-gathered C^T
     *bytes_per_gpu = b;
     return 0;
 }
@@ -1664,7 +1718,7 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
     {
         Shard& s = h->sh[0];
         h->stats.hbm_work_bytes =
-            8 * (s.in_cap + s.out_cap + 2 * s.ct_cap + s.dpart_cap + s.T_cap + s.T2_cap + s.ws_cap);
+            8 * (s.in_cap + s.out_cap + 2 * s.ct_cap + s.dpart_cap + s.T_cap + s.T2_cap + s.ws_cap + s.cg_cap);
     }
     return 0;
 }
