@@ -105,11 +105,29 @@ class JK:
         return tally if n_let is None else tally[n_let]
 
     @staticmethod
-    def build_JK(primary, auxiliary, do_wK: bool = False, doubles: int = 0, **options):
-        """JK::build_JK with SCF_TYPE=MEM_DF (jk.cc:143-150, export_fock.cc:50-57): a MemDFJK over the B200 engine
-        for psi4_b200 basis sets (integrals.BasisSet).  options: cutoff, condition, ngpu, omega, fit_on_device."""
+    def build_JK(primary, auxiliary, do_wK: bool = False, doubles: int = 0, scf_type: str = "MEM_DF", **options):
+        """JK::build_JK (jk.cc:72-234, export_fock.cc:50-57) for psi4_b200 basis sets (integrals.BasisSet).
+        scf_type "MEM_DF": a MemDFJK over the B200 engine (jk.cc:143-150).  scf_type "DF": the automatic choice of
+        jk.cc:206-229 -- the exact MEM_DF estimate from the Schwarz mask is compared with `doubles`; the reference then
+        falls back to DISK_DF, which does not exist behind the engine (its answer to "does not fit" is more Q shards),
+        so that case raises.  options: cutoff, condition, ngpu, omega, fit_on_device."""
         from . import scf
+        from .integrals import MintsHelper
 
+        scf_type = scf_type.upper()
+        if scf_type not in ("MEM_DF", "DF"):
+            raise PsiException("JK::build_JK: only SCF_TYPE MEM_DF (or DF resolving to it) is served by the B200 engine")
+        if scf_type == "DF":
+            est = DFHelper(primary.nbf(), auxiliary.nbf())
+            est.set_schwarz_cutoff(options.get("cutoff", 1.0e-12))
+            est.set_do_wK(do_wK)
+            est.set_Qshell_max(max(auxiliary.shell_nfunction(s) for s in range(auxiliary.nshell())))
+            est.prepare_sparsity(MintsHelper(primary.molecule(), primary).schwarz_function_maxima())
+            need = est.get_core_size(1)
+            if not need < doubles:  # jk.cc:213
+                raise PsiException(f"MemDFJK Memory: AOs need {need * 8 / 1024.0 ** 3:.3f} GiB; user supplied "
+                                   f"{doubles * 8 / 1024.0 ** 3:.3f} GiB.  The reference would switch to DiskDFJK here "
+                                   "(jk.cc:219-225); behind the B200 engine shard the tensor over more GPUs instead")
         jk = scf.build_jk(primary.molecule(), primary, auxiliary, do_wK=do_wK, **options)
         if doubles:
             jk.set_memory(doubles)

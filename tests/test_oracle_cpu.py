@@ -165,3 +165,23 @@ def test_memory_estimate_matches_reference_integers(basis):
     jk.set_do_wK(False)
     assert jk.name() == "MemDFJK"
     assert jk.memory_estimate() == a["mem_df_estimate_doubles"][basis]
+
+
+def test_build_jk_df_autoselect_follows_reference_threshold():
+    """jk.cc:206-229: SCF_TYPE=DF keeps MemDFJK iff memory_estimate() < doubles (strict).  Five Ar atoms / cc-pVDZ need
+    1 590 520 doubles (test_jkmemory.py:44): one double more is enough, exactly that many is not."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle_jk import OracleJK
+    from psi4_b200.integrals import BasisSet, Molecule
+    from psi4_b200.jk import JK, PsiException
+
+    mol = Molecule.from_angstrom(["Ar"] * 5, [[0, 0, z] for z in (0.0, 5.0, 15.0, 25.0, 35.0)])
+    P, A = BasisSet.build(mol, "cc-pvdz"), BasisSet.build(mol, "cc-pvdz-jkfit")
+    with pytest.raises(PsiException, match="DiskDFJK"):
+        JK.build_JK(P, A, doubles=1590520, scf_type="DF")
+    jk = JK.build_JK(P, A, doubles=1590521, scf_type="DF", jk_factory=lambda dfh, Ppq: OracleJK(dfh, Ppq))
+    assert jk.basisset() is P and jk.memory_ == 1590521
+    with pytest.raises(PsiException):
+        JK.build_JK(P, A, scf_type="PK")
