@@ -32,6 +32,54 @@ class DFHelper:
     def set_do_wK(self, do_wK: bool):
         self.do_wK_ = bool(do_wK)
 
+    def prepare_blocking(self, pshell_nfunction, Qshell_nfunction):
+        """dfhelper.cc:84-103: function offsets of the primary / auxiliary shells (pshell_aggs_, Qshell_aggs_) and the
+        largest auxiliary shell (Qshell_max_), from the per-shell function counts of the two basis sets."""
+        p = np.asarray(pshell_nfunction, dtype=np.int64)
+        q = np.asarray(Qshell_nfunction, dtype=np.int64)
+        if p.sum() != self.nbf_ or q.sum() != self.naux_:
+            raise ValueError("DFHelper: shell sizes do not add up to nbf / naux")
+        self.pshells_, self.Qshells_ = len(p), len(q)
+        self.pshell_aggs_ = np.concatenate([[0], np.cumsum(p)]).astype(np.uintp)
+        self.Qshell_aggs_ = np.concatenate([[0], np.cumsum(q)]).astype(np.uintp)
+        self.Qshell_max_ = int(q.max())
+
+    def pshell_blocks_for_AO_build(self, mem: int, symm: int = 1, hold_met: bool = False):
+        """dfhelper.cc:700-762 for the in-core (symm) case: consecutive primary shells are grouped while
+        block + full tensor + metric (or a second block buffer) fits in `mem` doubles.  Returns (steps, largest buffer,
+        largest block) with steps = [(first shell, last shell), ...] -- the p-blocks prepare_AO_core feeds to
+        compute_sparse_pQq_blocking_p_symm / contract_metric_AO_core_symm (:566-585), i.e. to b200jk_fit_rows."""
+        if not symm:
+            raise NotImplementedError("the on-disk blocking is out of scope (no DISK_DF behind the engine)")
+        full = int(self.big_skips_[self.nbf_])
+        steps, largest, block_size = [], 0, 0
+        i, count, total, tmpbs = 0, 0, 0, 0
+        scale = 3 if self.do_wK_ else 1
+        while i < self.pshells_:
+            count += 1
+            begin, end = int(self.pshell_aggs_[i]), int(self.pshell_aggs_[i + 1]) - 1
+            tmpbs += end - begin + 1
+            current = scale * int(self.symm_big_skips_[end + 1] - self.symm_big_skips_[begin])
+            total += current
+            constraint = total + full + (self.naux_ * self.naux_ if hold_met else total)
+            last = i == self.pshells_ - 1
+            if constraint > mem or last:
+                if count == 1 and not last:
+                    raise MemoryError("DFHelper: not enough memory for (p shell) AO blocking! required memory: "
+                                      f"{constraint * 8 / 1024.0 ** 3} [GiB].")
+                if constraint > mem:
+                    total -= current
+                    tmpbs -= end - begin + 1
+                    steps.append((i - count + 1, i - 1))
+                    i -= 1
+                elif last:
+                    steps.append((i - count + 1, i))
+                if largest < total:
+                    largest, block_size = total, tmpbs
+                count = total = tmpbs = 0
+            i += 1
+        return steps, largest, block_size
+
     def set_Qshell_max(self, qshell_max: int):
         """Qshell_max_ of prepare_blocking (dfhelper.cc:84-103): functions in the largest auxiliary shell."""
         self.Qshell_max_ = int(qshell_max)
@@ -50,6 +98,10 @@ class DFHelper:
         if not np.all(np.diag(keep)):
             raise ValueError("DFHelper: a diagonal pair is screened out (dfhelper.cc:3213 assumes it exists)")
         self.keep_ = keep
+        if getattr(self, "pshell_aggs_", None) is not None:
+            # schwarz_shell_mask_ (:374): a shell pair is significant iff any of its function pairs is
+            a = self.pshell_aggs_.astype(np.int64)
+            self.schwarz_shell_mask_ = np.add.reduceat(np.add.reduceat(keep.astype(np.int64), a[:-1], axis=0), a[:-1], axis=1) > 0
         count = np.cumsum(keep, axis=1)
         self.schwarz_fun_index_ = np.where(keep, count, 0).astype(np.uintp)       # :377-387
         sp = keep.sum(axis=1).astype(np.uintp)

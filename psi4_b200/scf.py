@@ -49,7 +49,8 @@ class DFTensors:
         self.mints = mints
         self.dfh = DFHelper(primary.nbf(), aux.nbf())
         self.dfh.set_schwarz_cutoff(cutoff)
-        self.dfh.set_Qshell_max(max(aux.shell_nfunction(s) for s in range(aux.nshell())))  # prepare_blocking :84-103
+        self.dfh.prepare_blocking([primary.shell_nfunction(s) for s in range(primary.nshell())],
+                                  [aux.shell_nfunction(s) for s in range(aux.nshell())])  # :84-103
         self.dfh.prepare_sparsity(fun_max_vals=mints.schwarz_function_maxima())   # prepare_sparsity :299-420
         metric = mints.metric(aux)                                                 # prepare_metric :1462-1476
         self.Jm12 = matrix_power(metric, -0.5, condition)                          # compute_metric :1491-1517

@@ -185,3 +185,38 @@ def test_build_jk_df_autoselect_follows_reference_threshold():
     assert jk.basisset() is P and jk.memory_ == 1590521
     with pytest.raises(PsiException):
         JK.build_JK(P, A, scf_type="PK")
+
+
+def test_pshell_blocking_tiles_the_primary_shells():
+    """pshell_blocks_for_AO_build (dfhelper.cc:700-762): blocks are consecutive, cover every primary shell once, each
+    respects the memory constraint it was cut by, and a budget below one shell's need throws like the reference."""
+    rng = np.random.default_rng(5)
+    psh = [1, 1, 3, 3, 5, 1, 3, 5, 7, 1, 3]
+    n, a = sum(psh), 40
+    r = rng.random((n, n))
+    keep = (r + r.T) < 1.2
+    np.fill_diagonal(keep, True)
+    d = DFHelper(n, a)
+    d.prepare_blocking(psh, [1, 3, 5, 7, 9, 15])
+    assert d.Qshell_max_ == 15 and int(d.pshell_aggs_[-1]) == n
+    d.prepare_sparsity(keep=keep)
+    sh = np.repeat(np.arange(len(psh)), psh)
+    want = np.zeros((len(psh), len(psh)), bool)
+    for i in range(n):
+        for j in range(n):
+            want[sh[i], sh[j]] |= keep[i, j]
+    assert np.array_equal(d.schwarz_shell_mask_, want)
+    full = int(d.big_skips_[n])
+    whole = int(d.symm_big_skips_[n])
+    steps, largest, block = d.pshell_blocks_for_AO_build(full + 2 * whole)
+    assert steps == [(0, len(psh) - 1)] and largest == whole and block == n
+    mem = full + 2 * whole // 3
+    steps, largest, block = d.pshell_blocks_for_AO_build(mem)
+    assert len(steps) > 1 and steps[0][0] == 0 and steps[-1][1] == len(psh) - 1
+    for (a0, a1), (b0, b1) in zip(steps, steps[1:]):
+        assert b0 == a1 + 1
+    for s0, s1 in steps:
+        cost = int(d.symm_big_skips_[int(d.pshell_aggs_[s1 + 1])] - d.symm_big_skips_[int(d.pshell_aggs_[s0])])
+        assert 2 * cost + full <= mem and cost <= largest
+    with pytest.raises(MemoryError):
+        d.pshell_blocks_for_AO_build(full + 10)
