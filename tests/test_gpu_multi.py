@@ -124,14 +124,17 @@ e = Engine(1); e.set_layout(n, a, d.small_skips_, d.big_skips_, d.schwarz_fun_in
 J, K, _ = e.compute([C], None, [C @ C.T])
 Jo, Ko, _, _ = oracle.build_JK(oracle.Sparsity(keep, a), P, [C])
 err = max(np.abs(J[0] - Jo[0]).max(), np.abs(K[0] - Ko[0]).max())
-print(f"LEGACY={os.environ.get('B200JK_LEGACY')} NOFUSE={os.environ.get('B200JK_NO_JFUSE')} err={err:.3e}")
+print(f"LEGACY={os.environ.get('B200JK_LEGACY')} NOFUSE={os.environ.get('B200JK_NO_JFUSE')} "
+      f"CGATHER={os.environ.get('B200JK_CGATHER')} err={err:.3e}")
 assert err < 1e-10
 """
 
 
-@pytest.mark.parametrize("env", [{"B200JK_LEGACY": "1"}, {"B200JK_NO_JFUSE": "1"}])
+@pytest.mark.parametrize("env", [{"B200JK_LEGACY": "1"}, {"B200JK_NO_JFUSE": "1"}, {"B200JK_CGATHER": "1"},
+                                 {"B200JK_CGATHER": "1", "B200JK_NO_JFUSE": "1"}])
 def test_ab_switches_still_correct(tmp_path, env):
-    """The A/B switches documented in DESIGN.md (first-generation kernels, unfused J) stay parity-green."""
+    """The A/B switches documented in DESIGN.md (first-generation kernels, unfused J, pre-gathered C^T forced on for a
+    small screened system, with and without the density row riding in it) stay parity-green."""
     script = tmp_path / "ab.py"
     script.write_text(LEGACY_SCRIPT)
     r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, B2_ROOT=ROOT, **env), capture_output=True,
