@@ -114,21 +114,31 @@ def cpu_baseline(cfg, keep, amp, C, Crl, slice_rows, steps=1, warmup=0):
     P = oracle.synth_fill(sp, 0, slice_rows, workloads.SEED, amp)
     Cl = [C] * cfg["nmat"]
     D = [C @ (C if Crl is None else Crl[i]).T for i in range(cfg["nmat"])]
+    # oracle/_ref/libref_dfjk.so = the reference's own DFHelper::build_JK and callees, compiled from its source by
+    # oracle/ref_build.py (prebuilt file on the GPU box); the C restatement is the fallback
+    try:
+        impl = "ref" if oracle.ref_lib() is not None else "port"
+    except Exception:  # a prebuilt library that does not load here: time the restatement instead
+        impl = "port"
     times, parts = [], None
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        _, _, _, tm = oracle.build_JK(sp, P, Cl, Crl, D=D, nthreads=cores)
+        _, _, _, tm = oracle.build_JK(sp, P, Cl, Crl, D=D, nthreads=cores, impl=impl)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
             parts = tm
     scale = naux / slice_rows
     ms = float(np.mean(times)) * 1e3 * scale
-    return {"value": ms, "unit": "ms", "cores": cores, "kind": "port",
-            "sample": f"oracle (C restatement of dfhelper.cc JK loops, OpenMP+OpenBLAS {cores} threads) on Q rows "
-                      f"[0,{slice_rows}) of naux={naux}, measured {np.mean(times) * 1e3:.1f} ms x {scale:.2f} (linear in Q)",
-            "J_ms": parts["J"] * 1e3 * scale, "K_ms": parts["K"] * 1e3 * scale,
-            "blas": oracle.lib().oracle_blas_config().decode()}, times
+    what = ("reference object code (DFHelper::build_JK and callees sliced from lib3index/dfhelper.cc, compiled unmodified; "
+            if impl == "ref" else "oracle (C restatement of dfhelper.cc JK loops; ")
+    out = {"value": ms, "unit": "ms", "cores": cores, "kind": "reference" if impl == "ref" else "port",
+           "sample": f"{what}OpenMP+OpenBLAS {cores} threads) on Q rows [0,{slice_rows}) of naux={naux}, measured "
+                     f"{np.mean(times) * 1e3:.1f} ms x {scale:.2f} (linear in Q)",
+           "blas": oracle.lib().oracle_blas_config().decode()}
+    if impl == "port":
+        out.update({"J_ms": parts["J"] * 1e3 * scale, "K_ms": parts["K"] * 1e3 * scale})
+    return out, times
 
 
 _OUT = None

@@ -1,8 +1,10 @@
 """Build the CPU oracle (test infrastructure) into oracle/_build/libdfjk_oracle.so.
 
-The reference path itself (lib3index/dfhelper.cc) cannot be compiled here: it includes
+The reference file as a whole (lib3index/dfhelper.cc) cannot be compiled here: it includes
 libmints/basisset.h -> <libint2/shell.h>, and Libint2 is neither installed nor vendored
-(SURVEY.md 8c).  So there is no oracle/_ref; the restatement in dfjk_oracle.c is the oracle.
+(SURVEY.md 8c).  The functions ON the J/K path never touch those headers, though: oracle/ref_build.py
+slices them out of the reference file at build time and compiles them into oracle/_ref/libref_dfjk.so,
+against which this restatement is checked bit for bit (tests/test_reference_slice.py).
 """
 import os
 import subprocess

@@ -71,6 +71,38 @@ def lib():
     return _lib
 
 
+_ref = None
+_JK_ARGTYPES = [
+    _sz, _sz, ct.c_int, _szp, _szp, _szp, _szp, _szp, _dp, _dp, _dp, ct.c_int,
+    ct.POINTER(_dp), ct.POINTER(_dp), ct.POINTER(ct.c_int), ct.POINTER(_dp),
+    ct.POINTER(_dp), ct.POINTER(_dp), ct.POINTER(_dp), ct.c_int, ct.c_int, ct.c_int, ct.c_int, _sz,
+]
+
+
+def ref_lib():
+    """oracle/_ref/libref_dfjk.so: the reference's own DFHelper functions compiled from /root/reference by
+    oracle/ref_build.py (None when neither the reference checkout nor a prebuilt library is present)."""
+    global _ref
+    if _ref is None:
+        import ref_build
+
+        path = ref_build.build()
+        if path is None:
+            return None
+        L = ct.CDLL(path)
+        L.ref_init.argtypes = [ct.c_char_p]
+        L.ref_build_JK.argtypes = _JK_ARGTYPES
+        L.ref_build_JK.restype = ct.c_int
+        L.ref_contract_metric_AO_core_symm.argtypes = [_sz, _sz, ct.c_int, _szp, _szp, _szp, _szp, _szp, _szp, _dp, _dp, _dp,
+                                                       _sz, _sz]
+        L.ref_contract_metric_AO_core_symm.restype = ct.c_int
+        if L.ref_init(find_openblas().encode()):
+            raise RuntimeError("ref_init failed")
+        lib()  # the BLAS thread controls live in the restatement's library (same OpenBLAS instance)
+        _ref = L
+    return _ref
+
+
 def _d(a):
     return a.ctypes.data_as(_dp)
 
@@ -154,7 +186,7 @@ def synth_dq(keep, naux, seed, amp, D):
 
 
 def contract_metric_AO_core_symm(sp: Sparsity, Qpq_sym: np.ndarray, metp: np.ndarray, Ppq: np.ndarray | None = None,
-                                 begin: int = 0, end: int | None = None, nthreads=None) -> np.ndarray:
+                                 begin: int = 0, end: int | None = None, nthreads=None, impl="port") -> np.ndarray:
     """dfhelper.cc:1653-1678 on the host: fitted + mirrored rows [begin, end] written into Ppq (allocated if None).
     Qpq_sym is relative to symm_big_skips[begin]."""
     L = lib()
@@ -168,7 +200,12 @@ def contract_metric_AO_core_symm(sp: Sparsity, Qpq_sym: np.ndarray, metp: np.nda
         Ppq = np.zeros(sp.packed_size)
     q = np.ascontiguousarray(Qpq_sym, dtype=np.float64)
     m = np.ascontiguousarray(metp, dtype=np.float64)
-    rc = L.oracle_contract_metric_AO_core_symm(sp.nbf, sp.naux, nthreads or L.oracle_max_threads(), _s(sp.fun_index),
+    fn = L.oracle_contract_metric_AO_core_symm
+    if impl == "ref":
+        if ref_lib() is None:
+            raise RuntimeError("oracle/_ref/libref_dfjk.so is not available")
+        fn = ref_lib().ref_contract_metric_AO_core_symm
+    rc = fn(sp.nbf, sp.naux, nthreads or L.oracle_max_threads(), _s(sp.fun_index),
                                                _s(sp.small_skips), _s(sp.big_skips), _s(sp.symm_small_skips),
                                                _s(sp.symm_ignored_columns), _s(sp.symm_big_skips), _d(q), _d(Ppq), _d(m),
                                                begin, end)
@@ -182,11 +219,14 @@ def _ptrs(arrs):
 
 
 def build_JK(sp: Sparsity, Ppq, Cleft, Cright=None, D=None, do_J=True, do_K=True, do_wK=False, m1Ppq=None, wPpq=None,
-             nthreads=None, q_block=0):
+             nthreads=None, q_block=0, impl="port"):
     """The reference's MemDFJK::compute_JK on host arrays.  Cright=None => lr_symmetric (jk.cc:597-602).
+    impl="port": the C restatement (dfjk_oracle.c); impl="ref": the reference's own functions (oracle/_ref).
 
     Returns (J, K, wK, timings) lists of (nbf,nbf) arrays (None where not tasked)."""
     L = lib()
+    if impl == "ref" and ref_lib() is None:
+        raise RuntimeError("oracle/_ref/libref_dfjk.so is not available (no reference checkout, nothing prebuilt)")
     n = sp.nbf
     nmat = len(Cleft)
     lr = Cright is None
@@ -204,16 +244,22 @@ def build_JK(sp: Sparsity, Ppq, Cleft, Cright=None, D=None, do_J=True, do_K=True
     wK = [np.zeros((n, n)) for _ in range(nmat)]
     nthreads = nthreads or L.oracle_max_threads()
     null = ct.cast(None, _dp)
-    rc = L.oracle_build_JK(
+    import time
+
+    t0 = time.perf_counter()
+    rc = (ref_lib().ref_build_JK if impl == "ref" else L.oracle_build_JK)(
         n, sp.naux, nthreads, _s(sp.fun_index), _s(sp.small_skips), _s(sp.big_skips), _s(sp.symm_small_skips),
         _s(sp.symm_ignored_columns), _d(Ppq), _d(m1Ppq) if m1Ppq is not None else null,
         _d(wPpq) if wPpq is not None else null, nmat, _ptrs(Cl), _ptrs(Cr), nocc, _ptrs(D), _ptrs(J), _ptrs(K),
         _ptrs(wK), int(do_J), int(do_K), int(do_wK), int(lr), int(q_block))
+    wall = time.perf_counter() - t0
     if rc:
-        raise RuntimeError(f"oracle_build_JK rc={rc}")
+        raise RuntimeError(f"{'ref' if impl == 'ref' else 'oracle'}_build_JK rc={rc}")
     t = np.zeros(4)
-    L.oracle_last_timings(_d(t))
-    return (J if do_J else None, K if do_K else None, wK if do_wK else None, {"J": t[0], "K": t[1], "wK": t[2]})
+    if impl != "ref":
+        L.oracle_last_timings(_d(t))
+    return (J if do_J else None, K if do_K else None, wK if do_wK else None,
+            {"J": t[0], "K": t[1], "wK": t[2], "total": wall})
 
 
 def compute_D(Cl, Cr):
