@@ -103,6 +103,30 @@ def ref_lib():
     return _ref
 
 
+def ref_sparsity_tables(fun_max_vals, naux, cutoff=1e-12, pshell_aggs=None):
+    """The table-building half of the reference's own prepare_sparsity (oracle/_ref) on given Schwarz maxima.
+    Returns a dict of the reference's member arrays."""
+    L = ref_lib()
+    if L is None:
+        raise RuntimeError("oracle/_ref/libref_dfjk.so is not available")
+    f = np.ascontiguousarray(fun_max_vals, dtype=np.float64)
+    n = f.shape[0]
+    aggs = np.arange(n + 1) if pshell_aggs is None else np.asarray(pshell_aggs, dtype=np.int64)
+    ps = len(aggs) - 1
+    shell = np.zeros((ps, ps))
+    for i in range(ps):
+        for j in range(ps):
+            shell[i, j] = f[aggs[i]:aggs[i + 1], aggs[j]:aggs[j + 1]].max()
+    out = {k: np.zeros(sz, dtype=np.uintp) for k, sz in
+           (("schwarz_fun_index_", n * n), ("small_skips_", n + 1), ("big_skips_", n + 1), ("symm_small_skips_", n),
+            ("symm_ignored_columns_", n), ("symm_big_skips_", n + 1), ("schwarz_shell_mask_", ps * ps))}
+    L.ref_prepare_sparsity_tables.argtypes = [_sz, _sz, _sz, ct.c_double, _dp, _dp, ct.c_double] + [_szp] * 7
+    rc = L.ref_prepare_sparsity_tables(n, naux, ps, cutoff, _d(shell), _d(f), float(f.max()), *[_s(v) for v in out.values()])
+    if rc:
+        raise RuntimeError(f"ref_prepare_sparsity_tables rc={rc}")
+    return out
+
+
 def _d(a):
     return a.ctypes.data_as(_dp)
 

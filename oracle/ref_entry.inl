@@ -110,6 +110,42 @@ int ref_build_JK(size_t nbf, size_t naux, int nthreads, const size_t* fun_index,
     return 0;
 }
 
+// Table-building half of DFHelper::prepare_sparsity (dfhelper.cc:370-420) on given Schwarz maxima; outputs sized like
+// the members: fun_index nbf*nbf, small_skips / big_skips / symm_big_skips nbf+1, the others nbf, shell_mask pshells^2.
+int ref_prepare_sparsity_tables(size_t nbf, size_t naux, size_t pshells, double cutoff, const double* shell_max_vals,
+                                const double* fun_max_vals, double max_val, size_t* fun_index, size_t* small_skips,
+                                size_t* big_skips, size_t* symm_small_skips, size_t* symm_ignored_columns,
+                                size_t* symm_big_skips, size_t* shell_mask) {
+    try {
+        psi::DFHelper d;
+        d.nbf_ = nbf;
+        d.naux_ = naux;
+        d.pshells_ = pshells;
+        d.cutoff_ = cutoff;
+        // the resizes of the function's first half (:306-314)
+        d.schwarz_shell_mask_.resize(pshells * pshells);
+        d.schwarz_fun_index_.resize(nbf * nbf);
+        d.symm_ignored_columns_.resize(nbf);
+        d.symm_big_skips_.resize(nbf + 1);
+        d.symm_small_skips_.resize(nbf);
+        d.small_skips_.resize(nbf + 1);
+        d.big_skips_.resize(nbf + 1);
+        std::vector<double> sm(shell_max_vals, shell_max_vals + pshells * pshells), fm(fun_max_vals, fun_max_vals + nbf * nbf);
+        d.prepare_sparsity_tables(sm, fm, max_val);
+        std::copy(d.schwarz_fun_index_.begin(), d.schwarz_fun_index_.end(), fun_index);
+        std::copy(d.small_skips_.begin(), d.small_skips_.end(), small_skips);
+        std::copy(d.big_skips_.begin(), d.big_skips_.end(), big_skips);
+        std::copy(d.symm_small_skips_.begin(), d.symm_small_skips_.end(), symm_small_skips);
+        std::copy(d.symm_ignored_columns_.begin(), d.symm_ignored_columns_.end(), symm_ignored_columns);
+        std::copy(d.symm_big_skips_.begin(), d.symm_big_skips_.end(), symm_big_skips);
+        std::copy(d.schwarz_shell_mask_.begin(), d.schwarz_shell_mask_.end(), shell_mask);
+        return d.sparsity_prepared_ ? 0 : 4;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "ref_prepare_sparsity_tables: %s\n", e.what());
+        return 3;
+    }
+}
+
 // DFHelper::contract_metric_AO_core_symm (dfhelper.cc:1653-1678)
 int ref_contract_metric_AO_core_symm(size_t nbf, size_t naux, int nthreads, const size_t* fun_index,
                                      const size_t* small_skips, const size_t* big_skips, const size_t* symm_small_skips,

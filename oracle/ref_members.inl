@@ -5,8 +5,10 @@
     std::string method_ = "STORE";
     std::unique_ptr<double[]> Ppq_, m1Ppq_, wPpq_;
     std::vector<size_t> small_skips_, big_skips_, symm_small_skips_, symm_ignored_columns_, symm_big_skips_;
-    std::vector<size_t> schwarz_fun_index_, Qshell_aggs_;
-    size_t Qshells_ = 0;
+    std::vector<size_t> schwarz_fun_index_, schwarz_shell_mask_, Qshell_aggs_;
+    size_t Qshells_ = 0, pshells_ = 0;
+    double cutoff_ = 1e-12;
+    bool sparsity_prepared_ = false;
     std::vector<std::string> AO_names_ = {"", ""};
     std::map<std::string, std::tuple<std::string, std::string>> files_;
     // ---- the disk / metric-file side is never reached by the in-core MEM_DF path: abort loudly if it were ----

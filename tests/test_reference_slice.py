@@ -133,3 +133,34 @@ def test_reference_object_code_reproduces_the_published_energies(ref):
     jk.initialize()
     assert abs(scf.UHF(mol, P, jk, multiplicity=3).compute_energy() - a["triplet_uhf_df"]) < 1e-8
     assert abs(scf.ROHF(mol, P, jk, multiplicity=3).compute_energy() - a["triplet_rohf_df"]) < 1e-8
+
+
+def test_sparsity_tables_match_reference_object_code(ref):
+    """prepare_sparsity's table half (dfhelper.cc:370-420), compiled from the reference, on real Schwarz maxima (five Ar
+    atoms / cc-pVDZ, the test_jkmemory system: 75.8 % of the pairs screened) and on random ones: mask rule, every index
+    table and the shell mask equal the host mirror (psi4_b200.DFHelper, what b200jk_set_layout is fed) and the
+    restatement's tables element for element."""
+    from psi4_b200.integrals import BasisSet, MintsHelper, Molecule
+
+    mol = Molecule.from_angstrom(["Ar"] * 5, [[0, 0, z] for z in (0.0, 5.0, 15.0, 25.0, 35.0)])
+    P = BasisSet.build(mol, "cc-pvdz")
+    cases = [(MintsHelper(mol, P).schwarz_function_maxima(), [P.shell_nfunction(s) for s in range(P.nshell())], 560, 1e-12)]
+    rng = np.random.default_rng(0)
+    f = 10.0 ** rng.uniform(-30, 0, (40, 40))
+    f = np.maximum(f, f.T)
+    np.fill_diagonal(f, 1.0)
+    cases.append((f, [1, 3, 5, 1, 3, 6, 10, 1, 3, 7], 33, 1e-9))
+    for fmax, psh, naux, cutoff in cases:
+        n = fmax.shape[0]
+        d = DFHelper(n, naux)
+        d.set_schwarz_cutoff(cutoff)
+        d.prepare_blocking(psh, [naux])
+        d.prepare_sparsity(fmax)
+        t = ref.ref_sparsity_tables(fmax, naux, cutoff, d.pshell_aggs_)
+        assert 0.0 < d.ao_sparsity() < 1.0
+        assert np.array_equal(t["schwarz_fun_index_"].reshape(n, n), d.schwarz_fun_index_)
+        for k in ("small_skips_", "big_skips_", "symm_small_skips_", "symm_ignored_columns_", "symm_big_skips_"):
+            assert np.array_equal(t[k], getattr(d, k)), k
+        assert np.array_equal(t["schwarz_shell_mask_"].reshape(len(psh), len(psh)).astype(bool), d.schwarz_shell_mask_)
+        sp = ref.Sparsity(d.keep_.astype(np.uint8), naux)
+        assert np.array_equal(sp.fun_index.reshape(n, n), d.schwarz_fun_index_) and np.array_equal(sp.big_skips, t["big_skips_"])
