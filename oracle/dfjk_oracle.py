@@ -103,6 +103,25 @@ def ref_lib():
     return _ref
 
 
+def ref_matrix_power(A, alpha, cutoff):
+    """Matrix::power (libmints/matrix.cc:2370-2424) as compiled from the reference: (A^alpha, eigenvalues kept)."""
+    import ref_build
+
+    path = ref_build.build_matrix()
+    if path is None:
+        raise RuntimeError("oracle/_ref/libref_matrix.so is not available")
+    L = ct.CDLL(path)
+    L.refm_init.argtypes = [ct.c_char_p]
+    L.refm_power.argtypes = [_dp, ct.c_int, ct.c_double, ct.c_double]
+    if L.refm_init(find_openblas().encode()):
+        raise RuntimeError("refm_init failed")
+    M = np.array(A, dtype=np.float64, order="C", copy=True)
+    kept = L.refm_power(_d(M), M.shape[0], float(alpha), float(cutoff))
+    if kept < 0:
+        raise RuntimeError(f"refm_power rc={kept}")
+    return M, kept
+
+
 def ref_sparsity_tables(fun_max_vals, naux, cutoff=1e-12, pshell_aggs=None):
     """The table-building half of the reference's own prepare_sparsity (oracle/_ref) on given Schwarz maxima.
     Returns a dict of the reference's member arrays."""

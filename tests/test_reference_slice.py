@@ -164,3 +164,32 @@ def test_sparsity_tables_match_reference_object_code(ref):
         assert np.array_equal(t["schwarz_shell_mask_"].reshape(len(psh), len(psh)).astype(bool), d.schwarz_shell_mask_)
         sp = ref.Sparsity(d.keep_.astype(np.uint8), naux)
         assert np.array_equal(sp.fun_index.reshape(n, n), d.schwarz_fun_index_) and np.array_equal(sp.big_skips, t["big_skips_"])
+
+
+def test_metric_power_matches_reference_object_code(ref):
+    """Matrix::power (libmints/matrix.cc:2370-2424) compiled from the reference vs the host driver's matrix_power
+    (scf.py): same eigenvalue cut (|lambda| < cutoff * |lambda|max dropped only for negative powers), same result on the
+    real fitting metric (A|B) of water / cc-pVDZ-jkfit and on a spectrum with one direction below the cut."""
+    from psi4_b200 import scf
+    from psi4_b200.integrals import BasisSet, MintsHelper, Molecule
+
+    mol = Molecule.from_zmat_h2o(0.96, 104.5)
+    P, A = BasisSet.build(mol, "cc-pvdz"), BasisSet.build(mol, "cc-pvdz-jkfit")
+    metric = MintsHelper(mol, P).metric(A)
+    for alpha in (-0.5, -1.0):  # mpower_ and wmpower_, dfhelper.h:356-357
+        R, kept = ref.ref_matrix_power(metric, alpha, 1e-10)
+        assert kept == A.nbf()
+        M = scf.matrix_power(metric, alpha, 1e-10)
+        assert np.abs(R - M).max() < 1e-9 * np.abs(R).max()
+    rng = np.random.default_rng(0)
+    V = np.linalg.qr(rng.standard_normal((24, 24)))[0]
+    w = 10.0 ** rng.uniform(-3, 0, 24)
+    w[5] = 1e-13 * w.max()
+    S = (V * w) @ V.T
+    S = 0.5 * (S + S.T)
+    R, kept = ref.ref_matrix_power(S, -0.5, 1e-10)
+    assert kept == 23  # the 1e-13 direction is dropped ...
+    assert np.abs(R - scf.matrix_power(S, -0.5, 1e-10)).max() < 1e-9 * np.abs(R).max()
+    R, kept = ref.ref_matrix_power(S, 0.5, 1e-10)
+    assert kept == 24  # ... but never for a positive power (matrix.cc:2403)
+    assert np.abs(R - scf.matrix_power(S, 0.5, 1e-10)).max() < 1e-9 * np.abs(R).max()
