@@ -89,7 +89,7 @@ def ref_lib():
         path = ref_build.build()
         if path is None:
             return None
-        L = ct.CDLL(path)
+        L = ct.CDLL(path, mode=os.RTLD_LAZY)  # libqt's unused Fortran externs stay unresolved
         L.ref_init.argtypes = [ct.c_char_p]
         L.ref_build_JK.argtypes = _JK_ARGTYPES
         L.ref_build_JK.restype = ct.c_int
@@ -110,7 +110,7 @@ def ref_matrix_power(A, alpha, cutoff):
     path = ref_build.build_matrix()
     if path is None:
         raise RuntimeError("oracle/_ref/libref_matrix.so is not available")
-    L = ct.CDLL(path)
+    L = ct.CDLL(path, mode=os.RTLD_LAZY)
     L.refm_init.argtypes = [ct.c_char_p]
     L.refm_power.argtypes = [_dp, ct.c_int, ct.c_double, ct.c_double]
     if L.refm_init(find_openblas().encode()):

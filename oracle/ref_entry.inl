@@ -2,11 +2,26 @@
 // oracle_build_JK / oracle_contract_metric_AO_core_symm (dfjk_oracle.c) so one Python wrapper drives both.
 #include <dlfcn.h>
 
-namespace psi {
-dgemm_fn REF_DGEMM = nullptr;
-dgemv_fn REF_DGEMV = nullptr;
-dcopy_fn REF_DCOPY = nullptr;
-}  // namespace psi
+// Fortran BLAS as the reference's libqt wrappers call it (FC_SYMBOL == 2: lower case + underscore), forwarded to the
+// OpenBLAS resolved by ref_init.  The other ~25 level-2/3 routines blas_intfc23.cc declares stay unresolved: nothing on
+// this path calls them (the library is loaded with lazy binding).
+typedef void (*dgemm_fn)(char*, char*, int*, int*, int*, double*, double*, int*, double*, int*, double*, double*, int*);
+typedef void (*dgemv_fn)(char*, int*, int*, double*, double*, int*, double*, int*, double*, double*, int*);
+typedef void (*dcopy_fn)(int*, double*, int*, double*, int*);
+static dgemm_fn REF_DGEMM = nullptr;
+static dgemv_fn REF_DGEMV = nullptr;
+static dcopy_fn REF_DCOPY = nullptr;
+extern "C" {
+void dgemm_(char* ta, char* tb, int* m, int* n, int* k, double* al, double* a, int* lda, double* b, int* ldb, double* be,
+            double* c, int* ldc) {
+    REF_DGEMM(ta, tb, m, n, k, al, a, lda, b, ldb, be, c, ldc);
+}
+void dgemv_(char* t, int* m, int* n, double* al, double* a, int* lda, double* x, int* incx, double* be, double* y,
+            int* incy) {
+    REF_DGEMV(t, m, n, al, a, lda, x, incx, be, y, incy);
+}
+void dcopy_(int* n, double* x, int* incx, double* y, int* incy) { REF_DCOPY(n, x, incx, y, incy); }
+}
 
 namespace {
 // the packed tensors are owned by the caller: hand them to the unique_ptr members for the call, take them back after
@@ -39,10 +54,10 @@ int ref_init(const char* blas_path) {
     const char* pre[] = {"scipy_", "", nullptr};
     for (int i = 0; pre[i]; i++) {
         std::string p = pre[i];
-        psi::REF_DGEMM = (psi::dgemm_fn)dlsym(h, (p + "dgemm_").c_str());
-        psi::REF_DGEMV = (psi::dgemv_fn)dlsym(h, (p + "dgemv_").c_str());
-        psi::REF_DCOPY = (psi::dcopy_fn)dlsym(h, (p + "dcopy_").c_str());
-        if (psi::REF_DGEMM && psi::REF_DGEMV && psi::REF_DCOPY) return 0;
+        REF_DGEMM = (dgemm_fn)dlsym(h, (p + "dgemm_").c_str());
+        REF_DGEMV = (dgemv_fn)dlsym(h, (p + "dgemv_").c_str());
+        REF_DCOPY = (dcopy_fn)dlsym(h, (p + "dcopy_").c_str());
+        if (REF_DGEMM && REF_DGEMV && REF_DCOPY) return 0;
     }
     return 2;
 }
@@ -55,7 +70,7 @@ int ref_build_JK(size_t nbf, size_t naux, int nthreads, const size_t* fun_index,
                  const double* Ppq, const double* m1Ppq, const double* wPpq, int nmat, double* const* Cleft,
                  double* const* Cright, const int* nocc, double* const* D, double* const* J, double* const* K,
                  double* const* wK, int do_J, int do_K, int do_wK, int lr_symmetric, size_t q_block) {
-    if (!psi::REF_DGEMM) return 1;
+    if (!REF_DGEMM) return 1;
     try {
         psi::DFHelper d;
         fill_tables(d, nbf, naux, nthreads, fun_index, small_skips, big_skips, symm_small_skips, symm_ignored_columns);
@@ -151,7 +166,7 @@ int ref_contract_metric_AO_core_symm(size_t nbf, size_t naux, int nthreads, cons
                                      const size_t* small_skips, const size_t* big_skips, const size_t* symm_small_skips,
                                      const size_t* symm_ignored_columns, const size_t* /*symm_big_skips*/,
                                      const double* Qpq, double* Ppq, const double* metp, size_t begin, size_t end) {
-    if (!psi::REF_DGEMM) return 1;
+    if (!REF_DGEMM) return 1;
     try {
         psi::DFHelper d;
         fill_tables(d, nbf, naux, nthreads, fun_index, small_skips, big_skips, symm_small_skips, symm_ignored_columns);

@@ -41,29 +41,12 @@ inline void free(double** m) {
 }  // namespace detail
 }  // namespace linalg
 
-typedef void (*dsyev_fn)(const char*, const char*, const int*, double*, const int*, double*, double*, const int*, int*);
-typedef void (*dscal_fn)(const int*, const double*, double*, const int*);
-typedef void (*dgemm_fn)(const char*, const char*, const int*, const int*, const int*, const double*, const double*,
-                         const int*, const double*, const int*, const double*, double*, const int*);
-extern dsyev_fn REFM_DSYEV;
-extern dscal_fn REFM_DSCAL;
-extern dgemm_fn REFM_DGEMM;
-
-// libqt/lapack_intfc.cc C_DSYEV, libqt/blas_intfc.cc C_DSCAL, libqt/blas_intfc23.cc:324-328 C_DGEMM
-inline int C_DSYEV(char jobz, char uplo, int n, double* a, int lda, double* w, double* work, int lwork) {
-    int info;
-    REFM_DSYEV(&jobz, &uplo, &n, a, &lda, w, work, &lwork, &info);
-    return info;
-}
-inline void C_DSCAL(size_t len, double alpha, double* x, int inc) {
-    int n = (int)len;
-    REFM_DSCAL(&n, &alpha, x, &inc);
-}
-inline void C_DGEMM(char transa, char transb, int m, int n, int k, double alpha, double* a, int lda, double* b, int ldb,
-                    double beta, double* c, int ldc) {
-    if (m == 0 || n == 0 || k == 0) return;
-    REFM_DGEMM(&transb, &transa, &n, &m, &k, &alpha, b, &ldb, a, &lda, &beta, c, &ldc);
-}
+// libqt's wrappers are the reference's own (lapack_intfc.cc C_DSYEV, blas_intfc.cc C_DSCAL, blas_intfc23.cc C_DGEMM,
+// compiled as they are and linked in); prototypes from libqt/qt.h.
+int C_DSYEV(char jobz, char uplo, int n, double* a, int lda, double* w, double* work, int lwork);
+void C_DSCAL(size_t len, double alpha, double* vec, int inc);
+void C_DGEMM(char transa, char transb, int m, int n, int k, double alpha, double* a, int lda, double* b, int ldb,
+             double beta, double* c, int ldc);
 
 class Matrix {
    public:

@@ -12,7 +12,7 @@
  *   outfile->Printf         libpsi4util/PsiOutStream.h
  *   timer_on / timer_off    libqt/qt.h:79-80
  *   PSIEXCEPTION            libpsi4util/exception.h:48
- *   C_DGEMM/C_DGEMV/C_DCOPY libqt/blas_intfc23.cc:324-328, :424-433, libqt/blas_intfc.cc (row-major over Fortran BLAS)
+ * (libqt's C_DGEMM / C_DGEMV / C_DCOPY are the reference's own, compiled from libqt/blas_intfc23.cc and blas_intfc.cc.)
  */
 #pragma once
 #include <algorithm>
@@ -60,29 +60,14 @@ inline void timer_on(const std::string&) {}
 inline void timer_off(const std::string&) {}
 #define PSIEXCEPTION(msg) std::runtime_error(msg)
 
-typedef void (*dgemm_fn)(const char*, const char*, const int*, const int*, const int*, const double*, const double*,
-                         const int*, const double*, const int*, const double*, double*, const int*);
-typedef void (*dgemv_fn)(const char*, const int*, const int*, const double*, const double*, const int*, const double*,
-                         const int*, const double*, double*, const int*);
-typedef void (*dcopy_fn)(const int*, const double*, const int*, double*, const int*);
-extern dgemm_fn REF_DGEMM;
-extern dgemv_fn REF_DGEMV;
-extern dcopy_fn REF_DCOPY;
-
-inline void C_DGEMM(char transa, char transb, int m, int n, int k, double alpha, double* a, int lda, double* b, int ldb,
-                    double beta, double* c, int ldc) {
-    if (m == 0 || n == 0 || k == 0) return;
-    REF_DGEMM(&transb, &transa, &n, &m, &k, &alpha, b, &ldb, a, &lda, &beta, c, &ldc);
-}
-inline void C_DGEMV(char trans, int m, int n, double alpha, double* a, int lda, double* x, int incx, double beta,
-                    double* y, int incy) {
-    if (m == 0 || n == 0) return;
-    trans = (trans == 'N' || trans == 'n') ? 'T' : 'N';
-    REF_DGEMV(&trans, &n, &m, &alpha, a, &lda, x, &incx, &beta, y, &incy);
-}
-inline void C_DCOPY(size_t length, double* x, int incx, double* y, int incy) {
-    int n = (int)length;
-    REF_DCOPY(&n, x, &incx, y, &incy);
-}
+// The BLAS wrappers are NOT stand-ins: libqt/blas_intfc23.cc (C_DGEMM :324-328, C_DGEMV :424-433) and
+// libqt/blas_intfc.cc (C_DCOPY) compile as they are (g++ -DFC_SYMBOL=2 on the reference files, see ref_build.py) and are
+// linked in; these are their prototypes (libqt/qt.h:100-, :160-).  The Fortran symbols they call (dgemm_, dgemv_, dcopy_)
+// are forwarded to the LP64 OpenBLAS bundled with scipy by ref_entry.inl.
+void C_DGEMM(char transa, char transb, int m, int n, int k, double alpha, double* a, int lda, double* b, int ldb,
+             double beta, double* c, int ldc);
+void C_DGEMV(char trans, int m, int n, double alpha, double* a, int lda, double* x, int incx, double beta, double* y,
+             int incy);
+void C_DCOPY(size_t length, double* x, int inc_x, double* y, int inc_y);
 
 }  // namespace psi
