@@ -193,3 +193,43 @@ def test_metric_power_matches_reference_object_code(ref):
     R, kept = ref.ref_matrix_power(S, 0.5, 1e-10)
     assert kept == 24  # ... but never for a positive power (matrix.cc:2403)
     assert np.abs(R - scf.matrix_power(S, 0.5, 1e-10)).max() < 1e-9 * np.abs(R).max()
+
+
+@pytest.mark.parametrize("puream", [True, False], ids=["spherical", "cartesian"])
+def test_dfjk_compare_with_real_integrals(ref, puream):
+    """tests/pytests/test_dfjk.py as it is written -- water (R = 1.00, 103.1 deg), cc-pVDZ / cc-pVDZ-jkfit, spherical
+    and cartesian, five random spaces, seven (C_left, C_right) pairs, C_right always added -- with REAL integrals from
+    the host front end.  The reference's counterpart to MemDFJK there is DiskDFJK, a different algorithm for the same
+    definition; here that role is played by the dense definition J/K = f(B), B = J^-1/2 (A|mn), and the MemDFJK side by
+    the reference's own object code and by the restatement.  Gate: the reference's 9 decimals."""
+    from oracle_jk import OracleJK
+    from psi4_b200.integrals import BasisSet, Molecule
+    from psi4_b200.jk import JK
+
+    mol = Molecule.from_zmat_h2o(1.00, 103.1)
+    primary = BasisSet.build(mol, "cc-pvdz", puream=puream)
+    aux = BasisSet.build(mol, "cc-pvdz-jkfit", puream=puream)
+    assert (primary.nbf(), aux.nbf()) == ((24, 116) if puream else (25, 131))
+    rng = np.random.default_rng(7)
+    sizes = [16, 16, 20, 20, 30]
+    spaces = [rng.random((primary.nbf(), s)) for s in sizes]
+    pairs = [[0, 0], [0, 1], [1, 1], [2, 2], [3, 2], [3, 3], [4, 4]]
+    results = {}
+    for impl in ("ref", "port"):
+        jk = JK.build_JK(primary, aux, jk_factory=lambda dfh, Ppq, impl=impl: OracleJK(dfh, Ppq, impl=impl))
+        jk.initialize()
+        for left, right in pairs:
+            jk.C_left_add(spaces[left])
+            jk.C_right_add(spaces[right])
+        jk.compute()
+        results[impl] = (jk.J(), jk.K())
+        dfh, Ppq = jk.dfh_, jk.Ppq
+    B = dfh.unpack(Ppq)  # (naux, nbf, nbf): nothing is screened in water, the packed tensor is the dense definition
+    assert dfh.ao_sparsity() == 0.0
+    for i, (left, right) in enumerate(pairs):
+        D = spaces[left] @ spaces[right].T
+        Jd = np.einsum("Qmn,Q->mn", B, np.einsum("Qls,ls->Q", B, D))
+        Kd = np.einsum("Qmi,Qni->mn", np.einsum("Qmn,ni->Qmi", B, spaces[left]), np.einsum("Qmn,ni->Qmi", B, spaces[right]))
+        for impl in ("ref", "port"):
+            assert np.abs(results[impl][0][i] - Jd).max() < 1e-9, f"J{i} {impl}"
+            assert np.abs(results[impl][1][i] - Kd).max() < 1e-9, f"K{i} {impl}"
