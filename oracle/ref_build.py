@@ -4,8 +4,8 @@ psi4 as a whole cannot be built in this image (Libint2 / LibXC / gau2grid / Eige
 lib3index/dfhelper.cc pulls their headers in through libmints), but the functions on the MEM_DF J/K path never touch
 them: they are loops over std::vector tables and three BLAS calls.  This recipe slices exactly those member-function
 definitions out of /root/reference/psi4/src/psi4/lib3index/dfhelper.cc at build time (located by signature, copied
-byte for byte into a generated translation unit under oracle/_ref/, which is git-ignored -- no reference source enters
-the repository), declares them in a stand-in `class DFHelper` whose members carry the reference's names and types
+byte for byte into a translation unit that exists only in memory and is piped to g++ -- no reference source is ever
+written into the repository tree; only the .so files land in the git-ignored oracle/_ref/), declares them in a stand-in `class DFHelper` whose members carry the reference's names and types
 (ref_members.inl), and compiles them against ref_shim.h together with the reference's libqt BLAS wrappers
 (libqt/blas_intfc23.cc, blas_intfc.cc -- whole files, unmodified).  Result: the arithmetic the restatement is checked against is
 the reference's own object code.
@@ -25,7 +25,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = "/root/reference/psi4/src/psi4/lib3index/dfhelper.cc"
 OUT = os.path.join(HERE, "_ref")
 LIB = os.path.join(OUT, "libref_dfjk.so")
-GEN = os.path.join(OUT, "ref_dfjk_gen.cc")
 FUNCTIONS = ["Qshell_blocks_for_JK_build", "contract_metric_AO_core_symm", "first_transform_pQq", "build_JK", "compute_JK",
              "compute_J_symm", "fill", "compute_J", "compute_J_combined", "compute_K", "compute_wK"]
 
@@ -76,14 +75,12 @@ def build_matrix(force: bool = False):
     text = open(REF_MATRIX_SRC).read()
     start = text.index("Dimension Matrix::power(double alpha, double cutoff) {")
     end = text.index("\n}\n", start) + 3
-    gen = os.path.join(OUT, "ref_matrix_gen.cc")
-    with open(gen, "w") as f:
-        f.write("// GENERATED by oracle/ref_build.py from " + REF_MATRIX_SRC + " -- do not commit\n")
-        f.write('#include "../ref_matrix_shim.h"\nnamespace psi {\n' + text[start:end] + '}  // namespace psi\n')
-        f.write('#include "../ref_matrix_entry.inl"\n')
-    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-w", "-o", LIB_MATRIX, gen, *LIBQT_FLAGS,
-                           os.path.join(LIBQT, "lapack_intfc.cc"), os.path.join(LIBQT, "blas_intfc.cc"),
-                           os.path.join(LIBQT, "blas_intfc23.cc"), "-ldl"])
+    src = ('#include "ref_matrix_shim.h"\nnamespace psi {\n' + text[start:end] + '}  // namespace psi\n'
+           '#include "ref_matrix_entry.inl"\n')
+    cmd = ["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-w", "-I" + HERE, "-o", LIB_MATRIX, *LIBQT_FLAGS, "-x", "c++", "-",
+           os.path.join(LIBQT, "lapack_intfc.cc"), os.path.join(LIBQT, "blas_intfc.cc"),
+           os.path.join(LIBQT, "blas_intfc23.cc"), "-ldl"]
+    subprocess.run(cmd, input=src.encode(), check=True)
     return LIB_MATRIX
 
 
@@ -97,20 +94,15 @@ def build(force: bool = False):
     os.makedirs(OUT, exist_ok=True)
     text = open(REF_SRC).read()
     decls, defs = zip(*(slice_function(text, f) for f in FUNCTIONS))
-    with open(GEN, "w") as f:
-        f.write("// GENERATED by oracle/ref_build.py from " + REF_SRC + " -- do not commit (oracle/_ref is git-ignored)\n")
-        f.write('#include "../ref_shim.h"\nnamespace psi {\nclass DFHelper {\n   public:\n#include "../ref_members.inl"\n')
-        for d in decls:
-            f.write("    " + " ".join(d.split()) + "\n")
-        f.write("    void prepare_sparsity_tables(std::vector<double>& shell_max_vals, std::vector<double>& fun_max_vals, "
-                "double max_val);\n};\n\n")
-        for d in defs:
-            f.write(d + "\n")
-        f.write(slice_sparsity_tables(text) + "\n")
-        f.write('}  // namespace psi\n#include "../ref_entry.inl"\n')
-    cmd = ["g++", "-O2", "-march=x86-64-v3", "-fopenmp", "-shared", "-fPIC", "-std=c++17", "-w", "-o", LIB, GEN,
-           *LIBQT_FLAGS, os.path.join(LIBQT, "blas_intfc23.cc"), os.path.join(LIBQT, "blas_intfc.cc"), "-ldl"]
-    subprocess.check_call(cmd)
+    src = ["// generated in memory by oracle/ref_build.py from " + REF_SRC + "; piped to g++, never written to disk",
+           '#include "ref_shim.h"', "namespace psi {", "class DFHelper {", "   public:", '#include "ref_members.inl"']
+    src += ["    " + " ".join(d.split()) for d in decls]
+    src += ["    void prepare_sparsity_tables(std::vector<double>& shell_max_vals, std::vector<double>& fun_max_vals, "
+            "double max_val);", "};", ""]
+    src += list(defs) + [slice_sparsity_tables(text), "}  // namespace psi", '#include "ref_entry.inl"', ""]
+    cmd = ["g++", "-O2", "-march=x86-64-v3", "-fopenmp", "-shared", "-fPIC", "-std=c++17", "-w", "-I" + HERE, "-o", LIB,
+           *LIBQT_FLAGS, "-x", "c++", "-", os.path.join(LIBQT, "blas_intfc23.cc"), os.path.join(LIBQT, "blas_intfc.cc"), "-ldl"]
+    subprocess.run(cmd, input="\n".join(src).encode(), check=True)
     return LIB
 
 

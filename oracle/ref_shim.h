@@ -1,8 +1,8 @@
 /*
  * ref_shim.h -- the little of psi4's runtime that the reference's own DF-JK loops touch, so that the function bodies
  * of lib3index/dfhelper.cc can be compiled UNMODIFIED, straight from /root/reference, into oracle/_ref/libref_dfjk.so
- * (recipe: oracle/ref_build.py, which slices the function definitions out of the reference file at build time; no
- * reference source is stored in this repository).
+ * (recipe: oracle/ref_build.py, which slices the function definitions out of the reference file at build time and pipes
+ * them to the compiler; no reference source is stored in this repository).
  *
  * TEST INFRASTRUCTURE ONLY: the library built from this is the checker of the checker -- tests compare the C
  * restatement (dfjk_oracle.c) with it bit for bit; bench.py may time it as the "reference" CPU baseline.
