@@ -83,7 +83,13 @@ int b200jk_upload(b200jk_t* h, int which, const double* host_pQq);
 
 /* Streaming variant for the p-blocked construction loop of prepare_AO_core (:540-587): rows
  * m in [m0, m1) only; host_rows points at the first double of row-block m0, i.e. what psi4 holds
- * at Ppq_ + big_skips[m0]. */
+ * at Ppq_ + big_skips[m0].
+ * Both producers (this call and b200jk_fit_rows) are pipelined: the call returns as soon as the caller's block has
+ * been READ -- a pageable block is copied into the engine's page-locked staging ring, a block inside a range
+ * registered with b200jk_register_host is DMA'd in place and the call waits for that copy only -- so the buffer may
+ * be refilled at once (psi4 reuses one block buffer, :553-585) while the transfer and the kernels run behind the
+ * call.  The block with m1 == nbf completes the tensor and drains the pipeline; compute / download calls are ordered
+ * behind whatever is still in flight. */
 int b200jk_upload_rows(b200jk_t* h, int which, size_t m0, size_t m1, const double* host_rows);
 
 /* ---- on-device fitting --------------------------------------------------------
