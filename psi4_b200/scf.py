@@ -375,3 +375,58 @@ class ROHF:
             C = X @ C2
         self.energy, self.C = E, C
         return E
+
+
+class CUHF(UHF):
+    """Constrained UHF (libscf_solver/cuhf.cc): the JK call pattern of UHF (both spin blocks in one jk.compute()), with
+    the spin-polarisation part of the Fock matrices projected so that core-virtual mixing vanishes in the basis of the
+    natural orbitals of the charge density (cuhf.cc:213-283).  Converges to the ROHF energy (tests/scf5 compares the
+    CUHF runs with the ROHF references)."""
+
+    def compute_energy(self) -> float:
+        X, S, H, jk, na, nb = self.X, self.S, self.H, self.jk, self.na, self.nb
+        Shalf = matrix_power(S, 0.5, 1e-10)
+
+        def diag(F):
+            _, C2 = np.linalg.eigh(X @ F @ X)
+            return X @ C2
+
+        C = diag(H)
+        Ca, Cb = np.ascontiguousarray(C[:, :na]), np.ascontiguousarray(C[:, :nb])
+        da, db = _DIIS(), _DIIS()
+        Eold = 0.0
+        for it in range(self.maxiter):
+            jk.C_clear()
+            jk.C_left_add(Ca)
+            jk.C_left_add(Cb)
+            jk.compute()
+            Jt = jk.J()[0] + jk.J()[1]
+            Fa, Fb = H + Jt - jk.K()[0], H + Jt - jk.K()[1]
+            Da, Db = Ca @ Ca.T, Cb @ Cb.T
+            E = self.Enuc + 0.5 * float(np.sum((Da + Db) * H) + np.sum(Da * Fa) + np.sum(Db * Fb))
+            # natural orbitals of the charge density in the orthogonal basis: occupations 1 (core), 1/2 (active), 0 (virtual)
+            occ, U = np.linalg.eigh(Shalf @ (0.5 * (Da + Db)) @ Shalf)
+            U = U[:, np.argsort(-occ)]
+            Fp = X @ (0.5 * (Fa + Fb)) @ X
+            Fm = U.T @ (X @ (0.5 * (Fa - Fb)) @ X) @ U
+            Fm[:nb, na:] = 0.0
+            Fm[na:, :nb] = 0.0
+            Fm = U @ Fm @ U.T
+            Xi = Shalf  # orthogonal-basis Fock -> AO basis: F = S^1/2 F' S^1/2
+            Fa, Fb = Xi @ (Fp + Fm) @ Xi, Xi @ (Fp - Fm) @ Xi
+            ga = X @ (Fa @ Da @ S - S @ Da @ Fa) @ X
+            gb = X @ (Fb @ Db @ S - S @ Db @ Fb) @ X
+            drms = float(np.sqrt(0.5 * (np.mean(ga ** 2) + np.mean(gb ** 2))))
+            self.iterations.append((E, E - Eold, drms))
+            if abs(E - Eold) < self.e_conv and drms < self.d_conv:
+                break
+            Eold = E
+            err = np.concatenate([ga.ravel(), gb.ravel()])
+            da.add(Fa, err)
+            db.add(Fb, err)
+            if it >= 1:
+                Fa, Fb = da.extrapolate(), db.extrapolate()
+            Ca = np.ascontiguousarray(diag(Fa)[:, :na])
+            Cb = np.ascontiguousarray(diag(Fb)[:, :nb])
+        self.energy = E
+        return E
