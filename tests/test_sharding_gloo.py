@@ -70,3 +70,48 @@ def test_q_ranges_tile_the_aux_index():
             assert all(edges[i][1] == edges[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in edges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _fit_worker(rank, world, port, out):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import dfjk_oracle as oracle
+    from psi4_b200 import DFHelper
+    from psi4_b200.sharding import q_range
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(11)
+    n, a = 26, 31
+    r = rng.random((n, n))
+    keep = (r + r.T) < 1.3
+    np.fill_diagonal(keep, True)
+    U = rng.standard_normal((a, n, n))
+    U = U + U.transpose(0, 2, 1)
+    g = rng.standard_normal((a, a))
+    met = g @ g.T / a + np.eye(a)
+    d = DFHelper(n, a)
+    d.prepare_sparsity(keep=keep)
+    # what b200jk_fit_rows does on shard `rank`: the WHOLE unfitted block, this shard's rows of the metric only
+    q0, q1 = q_range(a, rank, world)
+    mine = np.einsum("QR,Rmn->Qmn", met[q0:q1], U * keep[None])
+    rows = [None] * world  # shards are uneven (31 rows over 2 ranks): gather as objects
+    dist.all_gather_object(rows, mine)
+    if rank == 0:
+        sp = oracle.Sparsity(keep.astype(np.uint8), a)
+        ref = oracle.contract_metric_AO_core_symm(sp, d.pack_symm(U), met, nthreads=1)
+        got = d.pack(np.concatenate(rows))
+        with open(out, "w") as f:
+            f.write(repr(float(np.abs(got - ref).max())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_q_sharded_fitting_rows_concatenate_to_the_full_fit(tmp_path):
+    """On-device fitting at N > 1 (f2): every shard receives the whole unfitted block and contracts it with ITS rows of the
+    metric; the fitted tensor is the concatenation over shards -- no collective on the data path."""
+    out = str(tmp_path / "fit.txt")
+    mp.spawn(_fit_worker, args=(2, 29500 + (os.getpid() % 2000) + 7, out), nprocs=2, join=True)
+    assert float(open(out).read()) < 1e-11
