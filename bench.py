@@ -5,16 +5,22 @@ workload: C60 / cc-pVTZ DF-RHF (nbf 1800, naux 4740, nocc 180), synthetic tensor
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c60_tz] [--impl reference]
 
 One process per GPU (torchrun for N>1): the auxiliary index Q is sharded over the ranks and the
-partial J/K are summed by one NCCL all-reduce inside the engine ("strong" scaling: total work fixed).
+partial J/K are summed over NVLink inside the engine ("strong" scaling: total work fixed).
 
   value        ms per build with C/D/J/K resident in HBM (b200jk_compute_device), device time
                from CUDA events on the engine's stream, max over ranks
   e2e          ms per build through the host-pointer C ABI call b200jk_compute (what psi4's
                MemDFJK::compute_JK would call): pinned staging + H2D of C and D + D2H of J and K inside
   roofline     dominant kernel = K3 half-transform (DMMA); denominators: FP64 DMMA ceiling measured
-               live by a register-resident m8n8k4 loop (MEASURED_PEAKS.json has no FP64 figure)
-  cpu_baseline the oracle restatement of the reference's OpenMP+BLAS loops on this box's host cores,
-               on a Q-slice of the same workload, extrapolated linearly in naux (every hot loop is
+               live by a register-resident m8n8k4 loop (MEASURED_PEAKS.json has no FP64 figure), with a
+               cuBLAS DGEMM of the K-GEMM's shape timed beside it as the library comparator
+  parity_spot  outside the timed region, at every N: rows of J and a sample of K elements of rank 0's
+               summed result recomputed on the host from the counter hash that defines the synthetic
+               tensor (the oracle as CHECKER); the run exits non-zero above 1e-10
+  workloads    the other BASELINE.json configurations that fit this launch (n-C20H42 at every N,
+               (H2O)40 UHF at 8 GPUs), same measurements, C60 stays the headline `value`
+  cpu_baseline the reference's own object code (oracle/_ref) or the oracle restatement on this box's host
+               cores, on a Q-slice of the same workload, extrapolated linearly in naux (every hot loop is
                linear in the Q extent: dfhelper.cc:3193, :3208, :2183, :3374)
 """
 from __future__ import annotations
@@ -33,6 +39,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 METRIC = "DF-JK ms/SCF-iter at C60/cc-pVTZ"
+SPOT_TOL = 1e-10
 
 
 def parse():
@@ -44,6 +51,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-slice", type=int, default=0, help="Q rows in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="headline workload only (no `workloads` block, no cuBLAS calibration)")
+    ap.add_argument("--no-spot", action="store_true", help="skip the host-side spot parity (ncu / profiling runs)")
     ap.add_argument("--skip-probes", action="store_true", help="no FP64 ceiling probes (ncu launch lists); roofline.peak = last recorded")
     ap.add_argument("--nonsymmetric", action="store_true", help="C_right != C_left (general path)")
     ap.add_argument("--response", type=int, default=0, metavar="R",
@@ -93,13 +102,18 @@ class Clocks:
                 "power_w_max": max(pw) if pw else None, "samples": len(self.rows), "reasons": reasons}
 
 
+def _oracle():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dfjk_oracle as oracle  # bench.py may use oracle/ as the CPU baseline and as the checker, never as the product
+
+    return oracle
+
+
 # --------------------------------------------------------------------------------------------
-# CPU baseline: the oracle on a Q-slice of the same workload
+# CPU baseline: the reference's object code (or the oracle) on a Q-slice of the same workload
 # --------------------------------------------------------------------------------------------
 def cpu_baseline(cfg, keep, amp, C, Crl, slice_rows, steps=1, warmup=0):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import dfjk_oracle as oracle  # bench.py's cpu_baseline / --impl reference legs may use oracle/
-
+    oracle = _oracle()
     from psi4_b200 import workloads
 
     nbf, naux = cfg["nbf"], cfg["naux"]
@@ -134,11 +148,81 @@ def cpu_baseline(cfg, keep, amp, C, Crl, slice_rows, steps=1, warmup=0):
             if impl == "ref" else "oracle (C restatement of dfhelper.cc JK loops; ")
     out = {"value": ms, "unit": "ms", "cores": cores, "kind": "reference" if impl == "ref" else "port",
            "sample": f"{what}OpenMP+OpenBLAS {cores} threads) on Q rows [0,{slice_rows}) of naux={naux}, measured "
-                     f"{np.mean(times) * 1e3:.1f} ms x {scale:.2f} (linear in Q)",
+                     f"{np.mean(times) * 1e3:.1f} ms x {scale:.2f} (linear in Q; the per-m DGEMMs of the slice are skinnier "
+                     f"than at {naux} rows, so the extrapolation flatters the GPU)",
            "blas": oracle.lib().oracle_blas_config().decode()}
     if impl == "port":
         out.update({"J_ms": parts["J"] * 1e3 * scale, "K_ms": parts["K"] * 1e3 * scale})
     return out, times
+
+
+# --------------------------------------------------------------------------------------------
+# spot parity: rows of J and a sample of K recomputed on the host from the counter hash (checker only)
+# --------------------------------------------------------------------------------------------
+def spot_parity(keep, naux, amp, Cl, Crl, D, J, K, seed):
+    """max |J - J_ref| over four whole rows and max |K - K_ref| over the 4 x 4 elements they span, per density,
+    scaled by max(1, |ref|) as tests/test_gpu_fullsize.py does.  Cost: one pass of naux * kept-pairs hash
+    evaluations per density (seconds on the box's cores)."""
+    oracle = _oracle()
+    nbf = keep.shape[0]
+    keep8 = keep.astype(np.uint8)
+    rows = sorted({0, min(7, nbf - 1), min(nbf // 2 + 1, nbf - 1), nbf - 1})
+    t0 = time.perf_counter()
+    Bm = {m: oracle.synth_rowblock(keep8, naux, seed, amp, m) for m in rows}  # (naux, nbf) each
+    out = {"rows": rows, "max_abs_J": 0.0, "max_abs_K": 0.0, "max_scaled_J": 0.0, "max_scaled_K": 0.0, "k_elements": 0}
+    dq_cache = {}
+    for i in range(len(D)):
+        lr = Crl is None
+        Di = np.triu(D[i]) + np.triu(D[i], 1).T if lr else D[i]  # the symmetric path reads the upper triangle (:3188)
+        key = id(D[i])
+        if key not in dq_cache:
+            dq_cache[key] = oracle.synth_dq(keep8, naux, seed, amp, Di)
+        dq = dq_cache[key]
+        Tl = {m: Bm[m] @ Cl[i] for m in rows}
+        Tr = Tl if lr else {m: Bm[m] @ Crl[i] for m in rows}
+        for m in rows:
+            jref = Bm[m].T @ dq
+            dj = float(np.abs(J[i][m] - jref).max())
+            out["max_abs_J"] = max(out["max_abs_J"], dj)
+            out["max_scaled_J"] = max(out["max_scaled_J"], dj / max(1.0, float(np.abs(jref).max())))
+            for n in rows:
+                kref = float(np.vdot(Tl[m], Tr[n]))
+                dk = abs(float(K[i][m, n]) - kref)
+                out["max_abs_K"] = max(out["max_abs_K"], dk)
+                out["max_scaled_K"] = max(out["max_scaled_K"], dk / max(1.0, abs(kref)))
+                out["k_elements"] += 1
+    out["seconds"] = time.perf_counter() - t0
+    out["tolerance"] = SPOT_TOL
+    out["ok"] = bool(out["max_scaled_J"] < SPOT_TOL and out["max_scaled_K"] < SPOT_TOL)
+    return out
+
+
+def cublas_dgemm_calibration(nbf, kdim):
+    """cuBLAS DGEMM (through torch.mm on float64) at the K GEMM's own shape -- K = T T^T, nbf x nbf x kdim with both
+    operands k-contiguous, the full square as the reference's C_DGEMM('N','T') executes it (dfhelper.cc:3374) -- and
+    at 8192^3, on this box in this run.  The library comparator of kernels.k_gemm."""
+    import torch
+
+    out = {}
+    free, _ = torch.cuda.mem_get_info()
+    kd = int(min(kdim, (free * 0.5) // (8 * nbf)))
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    for tag, (m, k) in {"k_gemm_shape": (nbf, kd), "8192_cubed": (8192, 8192)}.items():
+        a = torch.randn((m, k), dtype=torch.float64, device="cuda", generator=gen)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        torch.mm(a, a.T)
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(3):
+            ev[0].record()
+            torch.mm(a, a.T)
+            ev[1].record()
+            torch.cuda.synchronize()
+            best = min(best, ev[0].elapsed_time(ev[1]))
+        out[tag] = {"m": m, "n": m, "k": k, "ms": best, "tflops": 2.0 * m * m * k / (best * 1e-3) / 1e12}
+        del a
+        torch.cuda.empty_cache()
+    return out
 
 
 _OUT = None
@@ -147,6 +231,258 @@ _OUT = None
 def emit(line):
     """The ONE JSON line of the contract, on the process's original stdout."""
     print(json.dumps(line), file=_OUT or sys.stdout, flush=True)
+
+
+class Dist:
+    """rank / world plumbing (torch.distributed over NCCL when launched by torchrun)."""
+
+    def __init__(self):
+        import torch
+
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the B200 JK engine has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+
+    def nccl_id(self, Engine):
+        if self.world == 1:
+            return None
+        torch = self.torch
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if self.rank == 0:
+            idt = torch.tensor(list(Engine.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        self.dist.broadcast(idt, 0)
+        return bytes(idt.cpu().tolist())
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max(self, x):
+        if not self.dist:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_true(self, flag):
+        return self.max(0.0 if flag else 1.0) == 0.0
+
+    def close(self):
+        if self.dist:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def make_inputs(args, name):
+    from psi4_b200 import workloads
+
+    cfg = dict(workloads.CONFIGS[name])
+    if args.response:
+        cfg["nmat"] = args.response
+    nbf, nocc, nmat = cfg["nbf"], cfg["nocc"], cfg["nmat"]
+    keep = workloads.pair_mask(nbf, cfg["mask"])
+    amp = workloads.amplitude(nbf)
+    nonsym = args.nonsymmetric or args.response
+    # one (C_left, C_right, D) triple per matrix.  RHF workloads pass the same pair nmat times; the UHF workload
+    # ((H2O)40, nmat = 2) gets two different occupied blocks (alpha / beta); --response: ONE C_left object and a
+    # different C_right per right-hand side.
+    if nmat > 1 and not args.response:
+        Cl = [workloads.orbitals(nbf, nocc, workloads.SEED + 10 * i) for i in range(nmat)]
+    else:
+        Cl = [workloads.orbitals(nbf, nocc)] * nmat
+    if args.response:
+        Crl = [workloads.orbitals(nbf, nocc, workloads.SEED + 1 + i) for i in range(nmat)]
+    elif nonsym:
+        Crl = [workloads.orbitals(nbf, nocc, workloads.SEED + 1)] * nmat
+    else:
+        Crl = None
+    D = [Cl[i] @ (Cl[i] if Crl is None else Crl[i]).T for i in range(nmat)]
+    return cfg, keep, amp, Cl, Crl, D
+
+
+def measure(args, ds, name, steps, warmup, headline):
+    """Device-resident arm + host-pointer arm + spot parity of one workload at this launch's N."""
+    from psi4_b200 import DFHelper, Engine, workloads
+
+    rank, world = ds.rank, ds.world
+    cfg, keep, amp, Cl, Crl, D = make_inputs(args, name)
+    nbf, naux, nocc, nmat = cfg["nbf"], cfg["naux"], cfg["nocc"], cfg["nmat"]
+    n2b = nbf * nbf * 8
+    d = DFHelper(nbf, naux)
+    d.prepare_sparsity(keep=keep)
+    t0 = time.perf_counter()
+    eng = Engine(rank=rank, world=world, device=ds.local_rank, nccl_id=ds.nccl_id(Engine))
+    eng.set_layout(nbf, naux, d.small_skips_, d.big_skips_, d.schwarz_fun_index_)
+    layout_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    eng.fill_synthetic(0, workloads.SEED, amp)
+    fill_s = time.perf_counter() - t0
+
+    # device operands mirror the host lists: a matrix passed twice is one buffer passed twice only under --response
+    # (the engine recognises a repeated C_left by identity there); otherwise every matrix gets its own copy
+    dC = [eng.dev_put(Cl[0])] * nmat if args.response else [eng.dev_put(x) for x in Cl]
+    dCr = None if Crl is None else [eng.dev_put(x) for x in Crl]
+    dD = [eng.dev_put(x) for x in D]
+    dJ = [eng.dev_alloc(n2b) for _ in range(nmat)]
+    dK = [eng.dev_alloc(n2b) for _ in range(nmat)]
+    noccs = [nocc] * nmat
+
+    pk_dmma = pk_dfma = None
+    if headline and rank == 0:
+        pk_dmma = eng.fp64_peak(0, 0.0 if args.skip_probes else 1.5)
+        pk_dfma = eng.fp64_peak(1, 0.0 if args.skip_probes else 0.5)
+
+    # ---- kernel-only arm: operands resident in HBM ----
+    for _ in range(warmup):
+        eng.compute_device(dC, dCr, noccs, dD, dJ, dK, None)
+    clocks = Clocks(ds.local_rank)
+    if rank == 0:
+        clocks.start()
+    ds.barrier()
+    w0 = time.perf_counter()
+    dev_ms, parts = 0.0, {"ms_j": 0.0, "ms_half": 0.0, "ms_kgemm": 0.0, "ms_allreduce": 0.0}
+    launches = 0
+    for _ in range(steps):
+        eng.compute_device(dC, dCr, noccs, dD, dJ, dK, None)
+        st = eng.stats()
+        dev_ms += st["ms_total"]
+        for k in parts:
+            parts[k] += st[k]
+        launches += st["launches"]
+    ds.barrier()
+    wall_ms = ds.max((time.perf_counter() - w0) * 1e3 / steps)
+    value = ds.max(dev_ms / steps)
+    for k in parts:
+        parts[k] = ds.max(parts[k] / steps)
+    st_dev = eng.stats()
+
+    # ---- end-to-end arm: host pointers through b200jk_compute ----
+    # D, J, K live in persistent caller matrices, as psi4's D_ao_/J_ao_/K_ao_ do (allocated once, jk.cc:355-446); the
+    # glue page-locks them once (b200jk_register_host).  C is a fresh pageable array every iteration and is staged.
+    for x in {id(x): x for x in D}.values():
+        eng.register_host(x)
+    # the SCF driver is one process: rank 0 reads the summed result, the other ranks only contribute to it
+    fetch = rank == 0
+    first = None
+    for _ in range(min(warmup, 2)):
+        J, K, _ = eng.compute(Cl, Crl, D, reuse_outputs=True, fetch=fetch)
+        if fetch and first is None:
+            first = ([x.copy() for x in J], [x.copy() for x in K])
+    ds.barrier()
+    w0 = time.perf_counter()
+    e2e_parts = {"ms_h2d": 0.0, "ms_d2h": 0.0}
+    for _ in range(steps):
+        J, K, _ = eng.compute(Cl, Crl, D, reuse_outputs=True, fetch=fetch)  # persistent J/K, as psi4's JK owns them
+        st = eng.stats()
+        launches += st["launches"]
+        for k in e2e_parts:
+            e2e_parts[k] += st[k] / steps
+    ds.barrier()
+    e2e_ms = ds.max((time.perf_counter() - w0) * 1e3 / steps)
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- determinism: the two arms, and the first and the last host-arm build, agree bit for bit ----
+    arms_equal = run_equal = True
+    if fetch:
+        for i in range(nmat):
+            arms_equal = arms_equal and np.array_equal(eng.dev_get(dJ[i], (nbf, nbf)), J[i]) \
+                and np.array_equal(eng.dev_get(dK[i], (nbf, nbf)), K[i])
+            if first is not None:
+                run_equal = run_equal and np.array_equal(first[0][i], J[i]) and np.array_equal(first[1][i], K[i])
+    # every rank's device-arm result is the same bits (the sum is formed once per element and broadcast)
+    import zlib
+
+    crc = float(zlib.crc32(eng.dev_get(dK[0], (nbf, nbf)).tobytes()))
+    ranks_equal = ds.max(crc) == -ds.max(-crc)
+
+    # ---- spot parity against the on-the-fly oracle (rank 0, outside every timed region) ----
+    spot = None
+    if fetch and not args.no_spot:
+        spot = spot_parity(keep, naux, amp, Cl, Crl, D, J, K, workloads.SEED)
+    ds.barrier()
+    reduce_kind = {0: "none (one GPU)", 1: "fixed-rank-order peer-memory kernel over NVLink (peer_reduce.cuh)",
+                   2: "NCCL all-reduce"}.get(st_dev["reduce_kind"], "?")
+    eng.close()
+    res = dict(cfg=cfg, keep=keep, amp=amp, Cl=Cl, Crl=Crl, value=value, wall_ms=wall_ms, parts=parts, st_dev=st_dev,
+               e2e_ms=e2e_ms, e2e_parts=e2e_parts, launches=launches, clk=clk, arms_equal=bool(arms_equal),
+               run_equal=bool(run_equal), ranks_equal=bool(ranks_equal), spot=spot, pk_dmma=pk_dmma, pk_dfma=pk_dfma,
+               layout_s=layout_s, fill_s=fill_s, reduce_kind=reduce_kind,
+               h2d=int(nmat * (Cl[0].nbytes * (1 if Crl is None else 2) + n2b)), d2h=int(nmat * 2 * n2b))
+    return res
+
+
+def kernel_table(res, peak_dmma, hbm_peak, peak_src):
+    parts, st = res["parts"], res["st_dev"]
+    half_tf = st["half_flops"] / (parts["ms_half"] * 1e-3) / 1e12 if parts["ms_half"] else 0.0
+    kg_tf = st["kgemm_flops"] / (parts["ms_kgemm"] * 1e-3) / 1e12 if parts["ms_kgemm"] else 0.0
+    j_gbs = st["j_bytes"] / (parts["ms_j"] * 1e-3) / 1e9 if parts["ms_j"] else 0.0
+    return {
+        "half_transform": {"ms": parts["ms_half"], "tflops": half_tf,
+                           "frac_of_dmma_peak": half_tf / peak_dmma if peak_dmma else None,
+                           "hbm_read_gbs": st["half_bytes"] / (parts["ms_half"] * 1e-3) / 1e9 if parts["ms_half"] else 0.0},
+        "k_gemm": {"ms": parts["ms_kgemm"], "tflops": kg_tf, "frac_of_dmma_peak": kg_tf / peak_dmma if peak_dmma else None},
+        "j_sweeps": {"ms": parts["ms_j"], "gbs": j_gbs, "frac_of_hbm_peak": j_gbs / hbm_peak, "hbm_peak_gbs": hbm_peak,
+                     "hbm_peak_source": peak_src},
+        "cross_gpu_sum": {"ms": parts["ms_allreduce"], "how": res["reduce_kind"]},
+    }, half_tf
+
+
+def single_process(args, cfg_name):
+    """psi4's situation: ONE process drives all GPUs (b200jk_create(ngpu)); only the host-pointer call exists here."""
+    from psi4_b200 import DFHelper, Engine, workloads
+
+    cfg, keep, amp, Cl, Crl, D = make_inputs(args, cfg_name)
+    nbf, naux, nocc, nmat = cfg["nbf"], cfg["naux"], cfg["nocc"], cfg["nmat"]
+    d = DFHelper(nbf, naux)
+    d.prepare_sparsity(keep=keep)
+    eng = Engine(args.gpus)
+    eng.set_layout(nbf, naux, d.small_skips_, d.big_skips_, d.schwarz_fun_index_)
+    eng.fill_synthetic(0, workloads.SEED, amp)
+    for x in {id(x): x for x in D}.values():
+        eng.register_host(x)
+    first = None
+    for _ in range(args.warmup):
+        J, K, _ = eng.compute(Cl, Crl, D, reuse_outputs=True)
+        if first is None:
+            first = ([x.copy() for x in J], [x.copy() for x in K])
+    dev_ms, launches, parts = 0.0, 0, {"ms_j": 0.0, "ms_half": 0.0, "ms_kgemm": 0.0, "ms_allreduce": 0.0}
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        J, K, _ = eng.compute(Cl, Crl, D, reuse_outputs=True)
+        st = eng.stats()
+        dev_ms += st["ms_total"] / args.steps
+        launches += st["launches"]
+        for k in parts:
+            parts[k] += st[k] / args.steps
+    e2e_ms = (time.perf_counter() - w0) * 1e3 / args.steps
+    run_equal = all(np.array_equal(a, b) for a, b in zip(first[0] + first[1], J + K))
+    spot = None if args.no_spot else spot_parity(keep, naux, amp, Cl, Crl, D, J, K, workloads.SEED)
+    n2b = nbf * nbf * 8
+    emit({
+        "metric": METRIC, "value": dev_ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": f"{cfg_name}: nbf={nbf} naux={naux} nocc={nocc} nmat={nmat}",
+                                        "q_sharding": f"Q split over {args.gpus} GPUs driven by ONE process"},
+        "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(args.gpus * nmat * (Cl[0].nbytes + n2b)),
+                "d2h_bytes_per_step": int(nmat * 2 * n2b)},
+        "gpu_launches": int(launches), "kernels_ms_max_over_gpus": parts, "mode": "single_process",
+        "run_to_run_bit_identical": bool(run_equal), "parity_spot": spot,
+        "cross_gpu_sum": {0: "none", 1: "peer-memory kernel", 2: "nccl"}.get(eng.stats()["reduce_kind"])})
+    ok = run_equal and (spot is None or spot["ok"])
+    eng.close()
+    return 0 if ok else 2
 
 
 def main():
@@ -159,182 +495,46 @@ def main():
     os.dup2(2, 1)
     from psi4_b200 import workloads
 
-    cfg = dict(workloads.CONFIGS[args.workload])
-    if args.response:
-        cfg["nmat"] = args.response
-    nbf, naux, nocc, nmat = cfg["nbf"], cfg["naux"], cfg["nocc"], cfg["nmat"]
-    keep = workloads.pair_mask(nbf, cfg["mask"])
-    amp = workloads.amplitude(nbf)
-    C = workloads.orbitals(nbf, nocc)
-    Cr = workloads.orbitals(nbf, nocc, workloads.SEED + 1) if (args.nonsymmetric or args.response) else None
-    # one (C_left, C_right, D) triple per matrix.  Default: the same pair nmat times, each uploaded and transformed on
-    # its own.  --response: ONE C_left object and a different C_right per right-hand side.
-    Cl = [C] * nmat
-    if args.response:
-        Crl = [workloads.orbitals(nbf, nocc, workloads.SEED + 1 + i) for i in range(nmat)]
-    else:
-        Crl = None if Cr is None else [Cr] * nmat
-    D = [C @ C.T] * nmat if Crl is None else ([C @ Cr.T] * nmat if not args.response else [C @ x.T for x in Crl])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": f"{args.workload}: nbf={nbf} naux={naux} nocc={nocc} nmat={nmat} "
-                          f"kept_pairs={int(keep.sum())} lr_symmetric={Cr is None} do_J=1 do_K=1"
-                          + (f" response: {nmat} right-hand sides share one C_left" if args.response else ""),
-              "pair_mask": workloads.mask_info(cfg["mask"]),
-              "q_sharding": f"Q split over {world} rank(s)" + ("; every rank uploads C/D, rank 0 reads J/K" if world > 1 else ""), "l2": "inputs_exceed_l2 (tensor shard >> 126 MB)"}
+
+    def config_of(name, cfg, keep, Crl):
+        return {"workload": f"{name}: nbf={cfg['nbf']} naux={cfg['naux']} nocc={cfg['nocc']} nmat={cfg['nmat']} "
+                            f"kept_pairs={int(keep.sum())} lr_symmetric={Crl is None} do_J=1 do_K=1"
+                            + (f" response: {cfg['nmat']} right-hand sides share one C_left" if args.response else ""),
+                "pair_mask": workloads.mask_info(cfg["mask"]),
+                "q_sharding": f"Q split over {world} rank(s)" + ("; every rank uploads C/D, rank 0 reads J/K" if world > 1 else ""),
+                "l2": "inputs_exceed_l2 (tensor shard >> 126 MB)"}
 
     if args.impl == "reference":
         if rank != 0:
-            return
-        cb, times = cpu_baseline(cfg, keep, amp, C, Crl, args.cpu_slice, steps=args.steps, warmup=args.warmup)
-        line = {"metric": METRIC, "value": cb["value"], "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": cb["value"], "higher_is_better": False, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "impl": "reference",
-                "cpu_baseline": cb,
-                "e2e": {"value": cb["value"], "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        emit(line)
-        return
+            return 0
+        cfg, keep, amp, Cl, Crl, D = make_inputs(args, args.workload)
+        cb, times = cpu_baseline(cfg, keep, amp, Cl[0], Crl, args.cpu_slice, steps=args.steps, warmup=args.warmup)
+        emit({"metric": METRIC, "value": cb["value"], "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
+              "warmup": args.warmup, "ms_per_step": cb["value"], "higher_is_better": False, "scaling": "strong",
+              "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(args.workload, cfg, keep, Crl),
+              "impl": "reference", "cpu_baseline": cb,
+              "e2e": {"value": cb["value"], "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+              "gpu_launches": 0})
+        return 0
 
-    import torch
-    import torch.distributed as dist
-
-    from psi4_b200 import DFHelper, Engine
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the B200 JK engine has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    nccl_id = None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt = torch.tensor(list(Engine.nccl_unique_id()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(idt, 0)
-        nccl_id = bytes(idt.cpu().tolist())
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    d = DFHelper(nbf, naux)
-    d.prepare_sparsity(keep=keep)
     if args.single_process and world == 1 and args.gpus > 1:
-        # psi4's situation: ONE process drives all GPUs (b200jk_create(ngpu)); only the host-pointer call exists here
-        eng = Engine(args.gpus)
-        eng.set_layout(nbf, naux, d.small_skips_, d.big_skips_, d.schwarz_fun_index_)
-        eng.fill_synthetic(0, workloads.SEED, amp)
-        for x in {id(x): x for x in D}.values():
-            eng.register_host(x)
-        for _ in range(args.warmup):
-            eng.compute(Cl, Crl, D, reuse_outputs=True)
-        dev_ms, launches, parts = 0.0, 0, {"ms_j": 0.0, "ms_half": 0.0, "ms_kgemm": 0.0, "ms_allreduce": 0.0}
-        w0 = time.perf_counter()
-        for _ in range(args.steps):
-            eng.compute(Cl, Crl, D, reuse_outputs=True)
-            st = eng.stats()
-            dev_ms += st["ms_total"] / args.steps
-            launches += st["launches"]
-            for k in parts:
-                parts[k] += st[k] / args.steps
-        e2e_ms = (time.perf_counter() - w0) * 1e3 / args.steps
-        n2b = nbf * nbf * 8
-        emit({
-            "metric": METRIC, "value": dev_ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": dict(config, q_sharding=f"Q split over {args.gpus} GPUs driven by ONE process"),
-            "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(args.gpus * nmat * (C.nbytes + n2b)),
-                    "d2h_bytes_per_step": int(nmat * 2 * n2b)},
-            "gpu_launches": int(launches), "kernels_ms_max_over_gpus": parts, "mode": "single_process"})
-        return
-    eng = Engine(rank=rank, world=world, device=local_rank, nccl_id=nccl_id)
-    eng.set_layout(nbf, naux, d.small_skips_, d.big_skips_, d.schwarz_fun_index_)
-    t0 = time.perf_counter()
-    eng.fill_synthetic(0, workloads.SEED, amp)
-    fill_s = time.perf_counter() - t0
+        return single_process(args, args.workload)
 
-    n2b = nbf * nbf * 8
-    # device operands mirror the host lists: a matrix passed twice is one buffer passed twice only under --response
-    # (the engine recognises a repeated C_left by identity there); otherwise every matrix gets its own copy
-    dC = [eng.dev_put(C)] * nmat if args.response else [eng.dev_put(C) for _ in range(nmat)]
-    dCr = None if Crl is None else [eng.dev_put(x) for x in Crl]
-    dD = [eng.dev_put(x) for x in D]
-    dJ = [eng.dev_alloc(n2b) for _ in range(nmat)]
-    dK = [eng.dev_alloc(n2b) for _ in range(nmat)]
-    noccs = [nocc] * nmat
+    ds = Dist()
+    res = measure(args, ds, args.workload, args.steps, args.warmup, headline=True)
 
-    pk_dmma = eng.fp64_peak(0, 0.0 if args.skip_probes else 1.5) if rank == 0 else None
-    pk_dfma = eng.fp64_peak(1, 0.0 if args.skip_probes else 0.5) if rank == 0 else None
-    # kernels timed inside a long step -> sustained ceiling (B200_PROFILING.md); the burst figure is reported too
-    peak_dmma = pk_dmma["sustained_tflops"] if pk_dmma else 0.0
-
-    # ---- kernel-only arm: operands resident in HBM ----
-    for _ in range(args.warmup):
-        eng.compute_device(dC, dCr, noccs, dD, dJ, dK, None)
-    clocks = Clocks(local_rank)
-    if rank == 0:
-        clocks.start()
-    barrier()
-    w0 = time.perf_counter()
-    dev_ms, parts = 0.0, {"ms_j": 0.0, "ms_half": 0.0, "ms_kgemm": 0.0, "ms_allreduce": 0.0}
-    launches = 0
-    for _ in range(args.steps):
-        eng.compute_device(dC, dCr, noccs, dD, dJ, dK, None)
-        st = eng.stats()
-        dev_ms += st["ms_total"]
-        for k in parts:
-            parts[k] += st[k]
-        launches += st["launches"]
-    barrier()
-    wall_ms = (time.perf_counter() - w0) * 1e3 / args.steps
-    value = max_over_ranks(dev_ms / args.steps)
-    wall_ms = max_over_ranks(wall_ms)
-    for k in parts:
-        parts[k] = max_over_ranks(parts[k] / args.steps)
-    st_dev = eng.stats()
-
-    # ---- end-to-end arm: host pointers through b200jk_compute ----
-    # D, J, K live in persistent caller matrices, as psi4's D_ao_/J_ao_/K_ao_ do (allocated once, jk.cc:355-446); the
-    # glue page-locks them once (b200jk_register_host).  C is a fresh pageable array every iteration and is staged.
-    for x in {id(x): x for x in D}.values():
-        eng.register_host(x)
-    # the SCF driver is one process: rank 0 reads the all-reduced result, the other ranks only contribute to it
-    fetch = rank == 0
-    for _ in range(min(args.warmup, 2)):
-        eng.compute(Cl, Crl, D, reuse_outputs=True, fetch=fetch)
-    barrier()
-    w0 = time.perf_counter()
-    e2e_parts = {"ms_h2d": 0.0, "ms_d2h": 0.0}
-    for _ in range(args.steps):
-        J, K, _ = eng.compute(Cl, Crl, D, reuse_outputs=True, fetch=fetch)  # persistent J/K, as psi4's JK owns them
-        st = eng.stats()
-        launches += st["launches"]
-        for k in e2e_parts:
-            e2e_parts[k] += st[k] / args.steps
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - w0) * 1e3 / args.steps)
-    clk = clocks.stop() if rank == 0 else None
-
-    # sanity: the two arms agree bit for bit (deterministic reductions)
-    Jd = eng.dev_get(dJ[0], (nbf, nbf))
-    Kd = eng.dev_get(dK[0], (nbf, nbf))
-    arms_equal = bool(np.array_equal(Jd, J[0]) and np.array_equal(Kd, K[0])) if fetch else True
+    # the other BASELINE.json configurations this launch can hold: same measurements, fewer steps
+    extra = {}
+    if not args.no_extra and args.workload == "c60_tz" and not (args.nonsymmetric or args.response):
+        names = ["c20h42_tz"] + (["h2o40_tz"] if world == 8 else [])
+        for nm in names:
+            extra[nm] = measure(args, ds, nm, max(3, min(args.steps, 5)), 3, headline=False)
 
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
+        ds.close()
+        return 0
 
     # ---- roofline of the dominant kernel (K3 half transform) + the others for context ----
     hbm_peak, peak_src = 6650.0, "fallback"
@@ -343,48 +543,72 @@ def main():
         hbm_peak, peak_src = float(mp["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         pass
-    half_tf = st_dev["half_flops"] / (parts["ms_half"] * 1e-3) / 1e12 if parts["ms_half"] else 0.0
-    kg_tf = st_dev["kgemm_flops"] / (parts["ms_kgemm"] * 1e-3) / 1e12 if parts["ms_kgemm"] else 0.0
-    j_gbs = st_dev["j_bytes"] / (parts["ms_j"] * 1e-3) / 1e9 if parts["ms_j"] else 0.0
+    pk_dmma, pk_dfma = res["pk_dmma"], res["pk_dfma"]
+    # kernels timed inside a long step -> sustained ceiling (B200_PROFILING.md); the burst figure is reported too
+    peak_dmma = pk_dmma["sustained_tflops"] if pk_dmma else 0.0
+    kernels, half_tf = kernel_table(res, peak_dmma, hbm_peak, peak_src)
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get("half_transform")
     except Exception:
         pass
-    roofline = {"kernel": "half_transform_kernel (K3)", "bound": "tensor", "achieved": half_tf, "peak": peak_dmma,
+    roofline = {"kernel": "half_ws_kernel (K3)", "bound": "tensor", "achieved": half_tf, "peak": peak_dmma,
                 "unit": "TFLOP/s", "frac": half_tf / peak_dmma if peak_dmma else None, "traffic": traffic,
+                "traffic_source": "profiles/traffic.json (ncu --set full capture of this kernel, recorded, not re-measured in this run)",
                 "peak_source": "sustained FP64 DMMA m8n8k4 register-resident loop (1.5 s back to back) measured live "
                                "on this GPU; no FP64 entry in MEASURED_PEAKS.json; datasheet 37-40 TFLOP/s",
-                "peak_burst": pk_dmma["burst_tflops"], "frac_of_burst": half_tf / pk_dmma["burst_tflops"],
+                "peak_burst": pk_dmma["burst_tflops"], "frac_of_burst": half_tf / pk_dmma["burst_tflops"] if pk_dmma["burst_tflops"] else None,
                 "dmma_probe": pk_dmma, "dfma_probe": pk_dfma}
-    kernels = {
-        "half_transform": {"ms": parts["ms_half"], "tflops": half_tf, "frac_of_dmma_peak": half_tf / peak_dmma if peak_dmma else None,
-                           "hbm_read_gbs": st_dev["half_bytes"] / (parts["ms_half"] * 1e-3) / 1e9 if parts["ms_half"] else 0.0},
-        "k_gemm": {"ms": parts["ms_kgemm"], "tflops": kg_tf, "frac_of_dmma_peak": kg_tf / peak_dmma if peak_dmma else None},
-        "j_sweeps": {"ms": parts["ms_j"], "gbs": j_gbs, "frac_of_hbm_peak": j_gbs / hbm_peak, "hbm_peak_gbs": hbm_peak,
-                     "hbm_peak_source": peak_src},
-        "allreduce": {"ms": parts["ms_allreduce"]},
-    }
+
+    cfg = res["cfg"]
+    if world == 1 and not args.no_extra:
+        try:
+            cal = cublas_dgemm_calibration(cfg["nbf"], cfg["naux"] * (cfg["nocc"] + cfg["nocc"] % 2))
+            kernels["k_gemm"]["cublas_dgemm_tflops"] = cal["k_gemm_shape"]["tflops"]
+            kernels["k_gemm"]["cublas_dgemm"] = cal
+            kernels["k_gemm"]["note"] = ("cuBLAS computes the full square (2 N^2 k flop); kgemm_ws_kernel is credited "
+                                         "N(N+1) k for the upper-triangle tiles it executes")
+        except Exception as ex:  # calibration must never cost the bench line
+            kernels["k_gemm"]["cublas_dgemm"] = {"error": str(ex)[:200]}
 
     cb = None
     if world == 1 and not args.no_cpu_baseline:
-        cb, _ = cpu_baseline(cfg, keep, amp, C, Crl, args.cpu_slice)
+        cb, _ = cpu_baseline(cfg, res["keep"], res["amp"], res["Cl"][0], res["Crl"], args.cpu_slice)
+
+    wl = {}
+    for nm, r in extra.items():
+        kt, _ = kernel_table(r, peak_dmma, hbm_peak, peak_src)
+        wl[nm] = {"config": config_of(nm, r["cfg"], r["keep"], r["Crl"]), "value_ms": r["value"], "e2e_ms": r["e2e_ms"],
+                  "kernels": kt, "parity_spot": r["spot"], "arms_bit_identical": r["arms_equal"],
+                  "run_to_run_bit_identical": r["run_equal"], "ranks_bit_identical": r["ranks_equal"],
+                  "gpu_launches": int(r["launches"]), "hbm_tensor_gb": r["st_dev"]["hbm_tensor_bytes"] / 1e9}
 
     line = {
-        "metric": METRIC, "value": value, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": value, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": config,
-        "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(nmat * (C.nbytes * (1 if Cr is None else 2) + n2b)),
-                "d2h_bytes_per_step": int(nmat * 2 * n2b), "ms_h2d": e2e_parts["ms_h2d"], "ms_d2h": e2e_parts["ms_d2h"]},
-        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb, "kernels": kernels, "clocks": clk,
-        "wall_ms_per_step": wall_ms, "arms_bit_identical": arms_equal,
-        "hbm": {"tensor_gb": st_dev["hbm_tensor_bytes"] / 1e9, "work_gb": st_dev["hbm_work_bytes"] / 1e9, "fill_s": fill_s},
+        "metric": METRIC, "value": res["value"], "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": res["value"], "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config_of(args.workload, cfg, res["keep"], res["Crl"]),
+        "e2e": {"value": res["e2e_ms"], "unit": "ms", "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"],
+                "ms_h2d": res["e2e_parts"]["ms_h2d"], "ms_d2h": res["e2e_parts"]["ms_d2h"]},
+        "gpu_launches": int(res["launches"]), "roofline": roofline, "cpu_baseline": cb, "kernels": kernels, "clocks": res["clk"],
+        "wall_ms_per_step": res["wall_ms"], "arms_bit_identical": res["arms_equal"],
+        "run_to_run_bit_identical": res["run_equal"], "ranks_bit_identical": res["ranks_equal"],
+        "parity_spot": res["spot"], "workloads": wl,
+        "hbm": {"tensor_gb": res["st_dev"]["hbm_tensor_bytes"] / 1e9, "work_gb": res["st_dev"]["hbm_work_bytes"] / 1e9,
+                "fill_s": res["fill_s"], "layout_s": res["layout_s"]},
     }
     emit(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    ds.close()
+    bad = []
+    for nm, r in [(args.workload, res)] + list(extra.items()):
+        if r["spot"] is not None and not r["spot"]["ok"]:
+            bad.append(f"{nm}: spot parity {r['spot']['max_scaled_J']:.2e} / {r['spot']['max_scaled_K']:.2e} above {SPOT_TOL}")
+        if not (r["arms_equal"] and r["run_equal"] and r["ranks_equal"]):
+            bad.append(f"{nm}: results not bit-identical (arms {r['arms_equal']}, run to run {r['run_equal']}, ranks {r['ranks_equal']})")
+    if bad:
+        print("bench.py: FAILED checks: " + "; ".join(bad), file=sys.stderr)
+        return 2
+    return 0
 
 
 if __name__ == "__main__":
-    main()
+    sys.exit(main())

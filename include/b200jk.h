@@ -168,6 +168,8 @@ typedef struct {
     uint64_t hbm_work_bytes;   /* bytes of HBM in work buffers                     */
     int n_shards;         /* local shards (GPUs driven by this handle)             */
     int q_begin, q_end;   /* Q range of local shard 0                              */
+    int reduce_kind;      /* cross-GPU sum: 0 none (one GPU), 1 fixed-rank-order peer-memory kernel over NVLink,
+                             2 NCCL all-reduce (B200JK_REDUCE=nccl, or no peer access between the devices) */
 } b200jk_stats;
 
 int b200jk_get_stats(const b200jk_t* h, b200jk_stats* out);

@@ -482,10 +482,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
 // ---------------------------------------------------------------------------------------------
 struct KgemmWsParams {
     int nbf, kdim, klen, ntiles, nitems;
-    int symmetric;      // T2 == T1: only tiles with tn >= tm are listed; diagonal tiles skip their lower half
+    int symmetric;      // T2 == T1: only tiles with tn >= tm are listed; diagonal tiles skip their lower-left quadrant
     const int2* tiles;  // [ntiles] (tm, tn)
     int* counter;
     double* ws;         // [nsplit][ntiles][128*128]
+    // Split-K reduction folded into the kernel: arrive[tile*8 + cw] counts the splits whose consumer warp cw has
+    // stored its part of the partial tile; the warp that makes it nsplit sums that part over all splits in split
+    // order (fixed order: deterministic, whoever arrives last) and accumulates it into K (beta = 1 across Q chunks),
+    // mirrored for T2 == T1.  nullptr: partials only, kgemm_reduce_list_kernel follows (B200JK_KREDUCE=separate).
+    int* arrive;        // [ntiles * 8], zeroed before launch
+    int nsplit;
+    double* K;          // [nbf][nbf]
 };
 
 __global__ void __launch_bounds__(WS_THREADS, 1)
@@ -553,9 +560,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         const int kb = (w / p.ntiles) * p.klen;
         const int ke = min(p.kdim, kb + p.klen);
         const int nkt = (ke - kb + BK - 1) / BK;
-        const int mbv = live_row_blocks(p.nbf - tl.x * BM, wm);
-        int nbv = max(0, min(NB, (p.nbf - (tl.y * BN + wn * 8 * NB) + 7) / 8));
-        // (diagonal tiles of a symmetric product are computed whole; the reduction keeps their upper triangle)
+        int mbv = live_row_blocks(p.nbf - tl.x * BM, wm);
+        const int nbv = max(0, min(NB, (p.nbf - (tl.y * BN + wn * 8 * NB) + 7) / 8));
+        // Diagonal tile of a symmetric product: its lower-left 64 x 64 quadrant (rows 64.., columns ..63) is the mirror
+        // of the upper-right one and is not computed -- the warps of the left column half stop after their first two
+        // row groups.  (The diagonal quadrants are still computed whole; only their upper triangles are kept.)
+        const bool diag = p.symmetric && tl.x == tl.y;
+        if (diag && wn == 0) mbv = min(mbv, 2);
         double acc[4][NB][2];
 #pragma unroll
         for (int a = 0; a < 4; a++)
@@ -570,6 +581,60 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
             for (int nb = 0; nb < NB; nb++) {
                 int c = wn * 8 * NB + nb * 8 + t * 2;
                 *reinterpret_cast<double2*>(wsp + r * BN + c) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+            }
+        }
+        if (p.arrive) {
+            const int tile = w % p.ntiles;
+            __threadfence();  // this lane's part of the partial tile is visible device-wide ...
+            __syncwarp();
+            int last = 0;
+            if (lane == 0) last = (atomicAdd(p.arrive + tile * WS_CONSUMER_WARPS + cw, 1) == p.nsplit - 1) ? 1 : 0;
+            last = __shfl_sync(0xffffffffu, last, 0);  // ... before the warp is counted
+            if (last) {
+                __threadfence();
+                // this warp's 32 x 64 part of the tile, summed over the splits in split order
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < NB; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+                for (int sp = 0; sp < p.nsplit; sp++) {
+                    const double* src = p.ws + ((size_t)sp * p.ntiles + tile) * (BM * BN);
+#pragma unroll
+                    for (int mb = 0; mb < 4; mb++) {
+                        if (mb < mbv) {
+                            const int r = mb * 32 + wm * 8 + gq;
+#pragma unroll
+                            for (int nb = 0; nb < NB; nb++) {
+                                if (nb < nbv) {
+                                    const int c = wn * 8 * NB + nb * 8 + t * 2;
+                                    const double2 v = __ldcg(reinterpret_cast<const double2*>(src + r * BN + c));
+                                    acc[mb][nb][0] += v.x;
+                                    acc[mb][nb][1] += v.y;
+                                }
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int mb = 0; mb < 4; mb++) {
+                    const int r = mb * 32 + wm * 8 + gq;
+                    const int m = tl.x * BM + r;
+                    if (mb < mbv && m < p.nbf) {
+#pragma unroll
+                        for (int nb = 0; nb < NB; nb++) {
+#pragma unroll
+                            for (int e = 0; e < 2; e++) {
+                                const int c = wn * 8 * NB + nb * 8 + t * 2 + e;
+                                const int n = tl.y * BN + c;
+                                if (nb < nbv && n < p.nbf && (!diag || c >= r)) {
+                                    const double v = acc[mb][nb][e];
+                                    p.K[(size_t)m * p.nbf + n] += v;
+                                    if (p.symmetric && n != m) p.K[(size_t)n * p.nbf + m] += v;
+                                }
+                            }
+                        }
+                    }
+                }
             }
         }
     }

@@ -25,6 +25,7 @@
 #include "dmma_ws.cuh"
 #include "fit_kernels.cuh"
 #include "j_kernels.cuh"
+#include "peer_reduce.cuh"
 
 using namespace b2k;
 
@@ -43,6 +44,7 @@ struct Nccl {
     int (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -60,7 +62,7 @@ struct Nccl {
         err = "libnccl lacks nccl" #f;                                   \
         return false;                                                    \
     }
-        SYM(GetUniqueId) SYM(CommInitRank) SYM(CommInitAll) SYM(CommDestroy) SYM(AllReduce) SYM(GroupStart)
+        SYM(GetUniqueId) SYM(CommInitRank) SYM(CommInitAll) SYM(CommDestroy) SYM(AllReduce) SYM(AllGather) SYM(GroupStart)
         SYM(GroupEnd) SYM(GetErrorString)
 #undef SYM
         return true;
@@ -69,6 +71,23 @@ struct Nccl {
 Nccl g_nccl;
 constexpr int kNcclDouble = 8;  // ncclFloat64
 constexpr int kNcclSum = 0;
+constexpr int kNcclMin = 3;
+constexpr int kNcclInt8 = 0, kNcclInt32 = 2;
+
+// Peer-memory window of one shard for the fixed-order cross-GPU sum (peer_reduce.cuh).  The window IS the shard's
+// partial-result buffer `out`; the flag block is a separate small allocation that never moves.
+struct PeerCtx {
+    unsigned* flags = nullptr;                 // own flag block: PR_CHANNELS x PR_FLAG_WORDS words
+    unsigned* status = nullptr;                // page-locked host word: a barrier of the peer sum timed out
+    unsigned* peer_flags[PR_MAXP] = {nullptr}; // every rank's flag block, mapped here (own entry = flags)
+    double* peer_win[PR_MAXP] = {nullptr};     // every rank's window, mapped here (own entry = out)
+    void* ipc_flags_base[PR_MAXP] = {nullptr}; // what cudaIpcOpenMemHandle returned (rank mode), to close later
+    void* ipc_win_base[PR_MAXP] = {nullptr};
+    void* xchg = nullptr;                      // device scratch of the handle exchange: world x 128 bytes
+    bool flags_open = false, win_open = false;
+    const double* win_key = nullptr;           // the `out` pointer the peers currently map
+    unsigned epoch[PR_CHANNELS] = {0, 0};
+};
 
 struct Phase {
     int tag;  // 0 J, 1 half, 2 kgemm, 3 allreduce, 4 h2d, 5 d2h, 6 total
@@ -124,6 +143,7 @@ struct Shard {
     double *T1 = nullptr, *T2 = nullptr, *ws = nullptr;
     size_t in_cap = 0, out_cap = 0, ct_cap = 0, dpart_cap = 0, T_cap = 0, T2_cap = 0, ws_cap = 0;
     ncclComm_t comm = nullptr;
+    PeerCtx peer;
     std::vector<Phase> phases;
     std::vector<cudaEvent_t> evpool;
     size_t evused = 0;
@@ -137,6 +157,7 @@ struct b200jk {
     std::vector<Shard> sh;
     int rank = 0, world = 1;  // rank mode (one shard per process) when world > 1 and sh.size()==1
     bool rank_mode = false;
+    int reduce_kind = 0;      // cross-GPU sum: 0 none (one GPU), 1 fixed-order peer-memory kernel, 2 NCCL all-reduce
     size_t nbf = 0, naux = 0;
     bool have_layout = false;
     bool uploaded[3] = {false, false, false};
@@ -252,6 +273,8 @@ struct PhaseScope {
 };
 
 inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
+
+#include "peer_host.inl"
 
 // Pick the split-K factor of the K GEMM: enough CTAs to fill 148 SMs in nearly whole waves while
 // each split keeps >= 64 k-tiles (prologue/epilogue amortised) and the partial-tile workspace stays bounded.
@@ -494,13 +517,25 @@ int run_kgemm_ws(b200jk* h, Shard& s, const double* T1, const double* T2, int kd
     p.tiles = tiles;
     p.counter = s.d_counter;
     p.ws = s.ws;
-    CK(cudaMemsetAsync(s.d_counter, 0, sizeof(int), s.stream));
+    // the split-K reduction runs inside the kernel (per-tile arrival counters behind the queue head);
+    // B200JK_KREDUCE=separate keeps the second pass for A/B measurement
+    static int separate = -1;
+    if (separate < 0) {
+        const char* e = getenv("B200JK_KREDUCE");
+        separate = (e && !strcmp(e, "separate")) ? 1 : 0;
+    }
+    p.arrive = separate ? nullptr : s.d_counter + 1;
+    p.nsplit = nsplit;
+    p.K = Kout;
+    CK(cudaMemsetAsync(s.d_counter, 0, sizeof(int) * (1 + (size_t)s.ntiles_full * WS_CONSUMER_WARPS), s.stream));
     kgemm_ws_kernel<<<std::min(p.nitems, s.nsm), WS_THREADS, smem, s.stream>>>(m1, m2, p);
     s.launches++;
     CK(cudaGetLastError());
-    kgemm_reduce_list_kernel<<<ntiles, 256, 0, s.stream>>>(s.ws, nsplit, ntiles, tiles, symmetric ? 1 : 0, p.nbf, Kout);
-    s.launches++;
-    CK(cudaGetLastError());
+    if (separate) {
+        kgemm_reduce_list_kernel<<<ntiles, 256, 0, s.stream>>>(s.ws, nsplit, ntiles, tiles, symmetric ? 1 : 0, p.nbf, Kout);
+        s.launches++;
+        CK(cudaGetLastError());
+    }
     return 0;
 }
 
@@ -592,6 +627,7 @@ int run_kgemm(b200jk* h, Shard& s, const double* T1, const double* T2, int kdim,
 
 // J sweeps of one density.  first_sweep_done: d_part was already produced by the fused half transform.
 int run_j(b200jk* h, Shard& s, const double* D, bool symmetric, double* Jout, double* dpart, bool first_sweep_done) {
+    if (s.nq == 0) return 0;  // an empty Q shard (naux < number of GPUs) contributes the zeros of the memset
     JParams p;
     p.tensor = s.tensor[B200JK_TENSOR_PPQ];
     p.row_off = s.d_row_off;
@@ -623,7 +659,7 @@ int run_j(b200jk* h, Shard& s, const double* D, bool symmetric, double* Jout, do
         s.launches++;
         CK(cudaGetLastError());
     }
-    j_dq_reduce_kernel<<<(s.nq + 127) / 128, 128, 0, s.stream>>>(dpart, p.nbf, s.nq, s.dvec);
+    j_dq_reduce_kernel<<<(s.nq + JR_Q - 1) / JR_Q, JR_Q * JR_M, 0, s.stream>>>(dpart, p.nbf, s.nq, s.dvec);
     s.launches++;
     CK(cudaGetLastError());
     j_mn_kernel<<<dim3((h->max_sp + 127) / 128, (unsigned)h->nbf), J_THREADS, sm2, s.stream>>>(p);
@@ -659,7 +695,14 @@ int ensure_work(b200jk* h, Shard& s, const Task& t, int* qc_out) {
     CK(cudaSetDevice(s.dev));
     int rc;
     size_t N = h->nbf;
-    if ((rc = grow(h, &s.out, &s.out_cap, (size_t)t.nmat * t.nprod * t.n2))) return rc;
+    {
+        size_t need = (size_t)t.nmat * t.nprod * t.n2;
+        const bool multi = h->sh.size() > 1 || (h->rank_mode && h->world > 1);
+        if (multi) need = std::max(need, kPeerBlockBytes / sizeof(double));  // its own IPC-exportable block
+        // rank mode: the peers map this buffer -- they let go of it (collectively) before it moves
+        if (need > s.out_cap && (rc = peer_close_windows(h))) return rc;
+        if ((rc = grow(h, &s.out, &s.out_cap, need))) return rc;
+    }
     if (t.do_J) {
         // one d_part per density: the fused half transforms of all densities run before the J sweeps
         if ((rc = grow(h, &s.dpart, &s.dpart_cap, (size_t)t.nmat * N * (size_t)s.nq + (size_t)s.nq))) return rc;
@@ -888,28 +931,6 @@ int collect_stats(b200jk* h) {
     return 0;
 }
 
-// Sum `count` doubles at s.out + off over all Q shards.  use_copy: issue on the copy stream (K results are
-// reduced and sent home while the J sweeps still run on the compute stream).
-int allreduce(b200jk* h, size_t off, size_t count, bool use_copy) {
-    bool multi = h->sh.size() > 1 || (h->rank_mode && h->world > 1);
-    if (!multi || !count) return 0;
-    if (h->sh.size() > 1) NK(g_nccl.GroupStart());
-    for (auto& s : h->sh) {
-        CK(cudaSetDevice(s.dev));
-        cudaStream_t st = use_copy ? s.copy : s.stream;
-        Phase ph;
-        ph.tag = 3;
-        ph.a = get_event(s);
-        ph.b = get_event(s);
-        CK(cudaEventRecord(ph.a, st));
-        NK(g_nccl.AllReduce(s.out + off, s.out + off, count, kNcclDouble, kNcclSum, s.comm, st));
-        CK(cudaEventRecord(ph.b, st));
-        s.phases.push_back(ph);
-    }
-    if (h->sh.size() > 1) NK(g_nccl.GroupEnd());
-    return 0;
-}
-
 // memcpy split over a few threads: the staging copies of D / J / K (tens of MB) otherwise cost more than the PCIe hop.
 void par_memcpy(void* dst, const void* src, size_t bytes) {
     const size_t chunk = (size_t)4 << 20;
@@ -1102,9 +1123,11 @@ int b200jk_create(b200jk_t** out, int ngpu, const int* dev_ids) {
         for (int i = 0; i < ngpu; i++) devs[i] = h->sh[i].dev;
         NK(g_nccl.CommInitAll(comms.data(), ngpu, devs.data()));
         for (int i = 0; i < ngpu; i++) h->sh[i].comm = comms[i];
+        if ((rc = peer_setup_local(h))) return rc;
     }
     h->world = ngpu;
     h->stats.n_shards = ngpu;
+    h->stats.reduce_kind = h->reduce_kind;
     return 0;
 }
 
@@ -1135,7 +1158,9 @@ int b200jk_create_rank(b200jk_t** out, int device, int rank, int world, const vo
         memcpy(&id, nccl_id, sizeof id);
         CK(cudaSetDevice(device));
         NK(g_nccl.CommInitRank(&h->sh[0].comm, world, id, rank));
+        if ((rc = peer_setup_rank(h))) return rc;
     }
+    h->stats.reduce_kind = h->reduce_kind;
     return 0;
 }
 
@@ -1153,8 +1178,14 @@ int b200jk_unregister_host(b200jk_t* h, void* ptr) {
     if (!h || !ptr) return B200JK_ERR_INVALID;
     for (size_t i = 0; i < h->pinned.size(); i++) {
         if (h->pinned[i].first == (const char*)ptr) {
-            CK(cudaHostUnregister(ptr));
+            // the bookkeeping entry goes whatever CUDA says (psi4 may already have freed the matrix): a stale range
+            // would make a later allocation at the same address look page-locked
+            cudaError_t e = cudaHostUnregister(ptr);
             h->pinned.erase(h->pinned.begin() + i);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return fail(h, B200JK_ERR_CUDA, "cudaHostUnregister: %s", cudaGetErrorString(e));
+            }
             return 0;
         }
     }
@@ -1168,6 +1199,7 @@ void b200jk_destroy(b200jk_t* h) {
         cudaEventDestroy(f.a);
         cudaEventDestroy(f.b);
     }
+    for (auto& s : h->sh) peer_free(h, s);
     for (auto& s : h->sh) free_shard(s);
     for (auto& sl : h->stage) {
         for (auto e : sl.done)
@@ -1187,8 +1219,27 @@ int b200jk_set_layout(b200jk_t* h, size_t nbf, size_t naux, const size_t* small_
     if (h->sh.empty()) return fail(h, B200JK_ERR_NODEVICE, "handle has no device");
     if (!nbf || !naux || !small_skips || !big_skips || !fun_index) return fail(h, B200JK_ERR_INVALID, "null/zero layout");
     if (nbf > 0x7fffffffu / 4 || naux > 0x7fffffffu / 4) return fail(h, B200JK_ERR_INVALID, "nbf/naux too large");
-    for (int w = 0; w < 3; w++)
-        if (h->uploaded[w]) return fail(h, B200JK_ERR_INVALID, "layout cannot change after upload");
+    // A second set_layout is a re-initialisation (jk.initialize() twice on one MemDFJK is legal in the reference and
+    // simply recomputes, MemDFJK.cc:71-96): the resident tensors, their TMA maps and everything sized by the old
+    // tables go; work buffers are kept (they are sized by capacity, not by shape).
+    for (auto& s : h->sh) {
+        CK(cudaSetDevice(s.dev));
+        CK(cudaStreamSynchronize(s.stream));
+        CK(cudaStreamSynchronize(s.copy));
+        for (int w = 0; w < 3; w++) {
+            if (s.tensor[w]) CK(cudaFree(s.tensor[w]));
+            if (s.d_amaps[w]) CK(cudaFree(s.d_amaps[w]));
+            s.tensor[w] = nullptr;
+            s.d_amaps[w] = nullptr;
+        }
+        if (s.d_cgmaps) CK(cudaFree(s.d_cgmaps));
+        s.d_cgmaps = nullptr;
+        s.cg_key_ptr = nullptr;
+        if (s.d_metric) CK(cudaFree(s.d_metric));
+        s.d_metric = nullptr;
+        s.have_metric = false;
+    }
+    for (int w = 0; w < 3; w++) h->uploaded[w] = false;
     h->nbf = nbf;
     h->naux = naux;
     h->small_skips.assign(small_skips, small_skips + nbf + 1);
@@ -1276,7 +1327,8 @@ int b200jk_set_layout(b200jk_t* h, size_t nbf, size_t naux, const size_t* small_
                 if ((rc = upload_vec(h, sym ? &s.d_tiles_sym : &s.d_tiles_full, tl))) return rc;
                 (sym ? s.ntiles_sym : s.ntiles_full) = (int)tl.size();
             }
-            std::vector<int> zero(1, 0);
+            // work-queue head + the K GEMM's per-(tile, consumer warp) arrival counters
+            std::vector<int> zero(1 + (size_t)s.ntiles_full * WS_CONSUMER_WARPS, 0);
             if ((rc = upload_vec(h, &s.d_counter, zero))) return rc;
         }
     }
@@ -1638,7 +1690,7 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
             CK(cudaSetDevice(h->sh[si].dev));
             CK(cudaStreamWaitEvent(h->sh[si].copy, evK[si], 0));
         }
-        if ((rc = allreduce(h, ol.offK, ol.countKW, true))) return rc;
+        if ((rc = reduce_shards(h, ol.offK, ol.countKW, true, 0, 0))) return rc;
         CK(cudaSetDevice(s0.dev));
         if (ol.countKW && fetch) {
             Phase ph;
@@ -1659,7 +1711,7 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
         }
         evKhome = get_event(s0);
         CK(cudaEventRecord(evKhome, s0.copy));
-        if ((rc = allreduce(h, ol.offJ, ol.countJ, false))) return rc;
+        if ((rc = reduce_shards(h, ol.offJ, ol.countJ, false, 1, 0))) return rc;
         CK(cudaSetDevice(s0.dev));
         if (ol.countJ && fetch) {
             PhaseScope ps(s0, 5);
@@ -1678,7 +1730,9 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
             CK(cudaStreamWaitEvent(s.stream, e, 0));
         }
     } else {
-        if ((rc = allreduce(h, 0, ol.total, false))) return rc;
+        // the same two sums as the host-operand arm (K group, then J group), result on every rank
+        if ((rc = reduce_shards(h, ol.offK, ol.countKW, false, 0, -1))) return rc;
+        if ((rc = reduce_shards(h, ol.offJ, ol.countJ, false, 1, -1))) return rc;
         CK(cudaSetDevice(s0.dev));
         size_t off = 0;
         for (int pr = 0; pr < 3; pr++) {
@@ -1712,8 +1766,10 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
     if (host_ops && do_J && fetch)
         for (int i = 0; i < nmat; i++)
             if (!is_pinned(h, J[i], n2 * 8)) par_memcpy(J[i], h->pin_out + ol.offJ + (size_t)i * n2, n2 * 8);
+    if ((rc = peer_check_status(h))) return rc;
     account_work(h, t);
     collect_stats(h);
+    h->stats.reduce_kind = h->reduce_kind;
     h->stats.hbm_work_bytes = 0;
     {
         Shard& s = h->sh[0];

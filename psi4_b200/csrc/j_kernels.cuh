@@ -88,20 +88,33 @@ __global__ void __launch_bounds__(J_THREADS) j_dq_kernel(JParams p) {
     }
 }
 
-// d[q] = sum_m dpart[m][q], fixed order (deterministic; replaces the serial thread reduce :3197-3199).
-__global__ void j_dq_reduce_kernel(const double* __restrict__ dpart, int nbf, int nq, double* __restrict__ d) {
-    int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    int m = 0;
-    for (; m + 3 < nbf; m += 4) {
-        s0 += dpart[(size_t)m * nq + q];
-        s1 += dpart[(size_t)(m + 1) * nq + q];
-        s2 += dpart[(size_t)(m + 2) * nq + q];
-        s3 += dpart[(size_t)(m + 3) * nq + q];
+// d[q] = sum_m dpart[m][q] in a fixed order (deterministic; replaces the serial thread reduce :3197-3199).
+// block = 32 q x 32 m-slices: slice y sums m = y, y+32, ... into shared memory, then the 32 slice sums of a q are
+// added in slice order.  (One thread per q walking all nbf rows left a handful of CTAs on a latency-bound loop: at
+// 592 Q rows per GPU that was ~0.2 ms of a 1.2 ms J phase.)
+constexpr int JR_Q = 32, JR_M = 32;
+__global__ void __launch_bounds__(JR_Q * JR_M) j_dq_reduce_kernel(const double* __restrict__ dpart, int nbf, int nq,
+                                                                   double* __restrict__ d) {
+    __shared__ double part[JR_M][JR_Q + 1];
+    const int qx = threadIdx.x & (JR_Q - 1), my = threadIdx.x / JR_Q;
+    const int q = blockIdx.x * JR_Q + qx;
+    double s0 = 0, s1 = 0;
+    if (q < nq) {
+        int m = my;
+        for (; m + JR_M < nbf; m += 2 * JR_M) {
+            s0 += dpart[(size_t)m * nq + q];
+            s1 += dpart[(size_t)(m + JR_M) * nq + q];
+        }
+        if (m < nbf) s0 += dpart[(size_t)m * nq + q];
     }
-    for (; m < nbf; m++) s0 += dpart[(size_t)m * nq + q];
-    d[q] = (s0 + s1) + (s2 + s3);
+    part[my][qx] = s0 + s1;
+    __syncthreads();
+    if (my == 0 && q < nq) {
+        double s = 0.0;
+#pragma unroll
+        for (int y = 0; y < JR_M; y++) s += part[y][qx];
+        d[q] = s;
+    }
 }
 
 // Density operand of the fused first sweep (half_ws_kernel): Dm[m][n] = D[m][n], or, for lr_symmetric builds,

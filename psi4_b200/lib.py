@@ -27,6 +27,7 @@ class Stats(ct.Structure):
         ("j_bytes", ct.c_double), ("half_flops", ct.c_double), ("half_bytes", ct.c_double),
         ("kgemm_flops", ct.c_double), ("launches", ct.c_uint64), ("hbm_tensor_bytes", ct.c_uint64),
         ("hbm_work_bytes", ct.c_uint64), ("n_shards", ct.c_int), ("q_begin", ct.c_int), ("q_end", ct.c_int),
+        ("reduce_kind", ct.c_int),
     ]
 
     def as_dict(self):
@@ -148,6 +149,9 @@ class Engine:
                                              fi.ctypes.data_as(_szp)))
         self.nbf, self.naux = int(nbf), int(naux)
         self._small_skips, self._big_skips = ss, bs
+        # symm_big_skips_ (dfhelper.cc:413-416): offsets of the symmetric-packed blocks fit_rows takes
+        mi = np.triu(fi.reshape(int(nbf), int(nbf)) > 0).sum(axis=1)
+        self._symm_big_skips = np.concatenate(([0], np.cumsum(mi * int(naux)))).astype(np.uintp)
 
     def upload(self, which, packed):
         p = np.ascontiguousarray(packed, dtype=np.float64)
@@ -174,6 +178,9 @@ class Engine:
     def fit_rows(self, which, m0, m1, sym_rows):
         """Unfitted symmetric-packed rows [m0, m1) -> fitted, mirrored rows of tensor `which` (on the device)."""
         p = np.ascontiguousarray(sym_rows, dtype=np.float64)
+        need = int(self._symm_big_skips[m1] - self._symm_big_skips[m0])
+        if p.size != need:
+            raise B200JKError(1, f"symmetric-packed block has {p.size} doubles, layout says {need}")
         self._check(self.L.b200jk_fit_rows(self.h, which, m0, m1, _d(p)))
 
     def fit_stats(self) -> dict:

@@ -17,10 +17,10 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-def _case(rng, oracle):
+def _case(rng, oracle, n=90):
     from psi4_b200 import DFHelper
 
-    n, a = 90, 131
+    a = 131
     r = rng.random((n, n))
     keep = (r + r.T) < 1.4
     np.fill_diagonal(keep, True)
@@ -35,13 +35,14 @@ def _case(rng, oracle):
 
 
 @pytest.mark.parametrize("lr", [True, False])
-def test_single_process_multi_gpu(oracle, lr):
+@pytest.mark.parametrize("n", [90, 91])  # 91: odd nbf^2 -> the cross-GPU sum takes its unaligned (8-byte) path
+def test_single_process_multi_gpu(oracle, lr, n):
     if _ngpu() < 2:
         pytest.skip("needs >= 2 GPUs")
     from psi4_b200 import Engine
 
     rng = np.random.default_rng(8)
-    d, sp, P, Cl, Cr = _case(rng, oracle)
+    d, sp, P, Cl, Cr = _case(rng, oracle, n)
     Cr = None if lr else Cr
     D = [x @ (x if lr else y).T for x, y in zip(Cl, Cl if lr else Cr)]
     Jo, Ko, _, _ = oracle.build_JK(sp, P, Cl, Cr, D=D)
@@ -54,6 +55,10 @@ def test_single_process_multi_gpu(oracle, lr):
             assert np.abs(J[i] - Jo[i]).max() < 1e-10
             assert np.abs(K[i] - Ko[i]).max() < 1e-10
         assert e.stats()["n_shards"] == ng
+        assert e.stats()["reduce_kind"] == 1  # the fixed-order peer-memory sum, not NCCL
+        # deterministic: a second build gives the same bits
+        J2, K2, _ = e.compute(Cl, Cr, D)
+        assert all(np.array_equal(a, b) for a, b in zip(J + K, J2 + K2))
         e.close()
 
 
@@ -72,7 +77,7 @@ idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
 if rank == 0:
     idt = torch.tensor(list(Engine.nccl_unique_id()), dtype=torch.uint8, device="cuda")
 dist.broadcast(idt, 0)
-d, sp, P, Cl, Cr = _case(np.random.default_rng(8), oracle)
+d, sp, P, Cl, Cr = _case(np.random.default_rng(8), oracle, int(os.environ.get("B2_NBF", "90")))
 e = Engine(rank=rank, world=world, device=lrk, nccl_id=bytes(idt.cpu().tolist()))
 e.set_layout(d.nbf_, d.naux_, d.small_skips_, d.big_skips_, d.schwarz_fun_index_)
 e.upload(0, P)   # every rank holds the host tensor here; the engine copies only its Q shard
@@ -89,23 +94,45 @@ if rank == 0:
 else:
     assert J2 is None and K2 is None
 print(f"RANK{rank} fetch_ok", flush=True)
+want_kind = 2 if os.environ.get("B200JK_REDUCE") == "nccl" else 1
+assert st["reduce_kind"] == want_kind, st["reduce_kind"]
+# determinism (SURVEY.md 8e): run to run, and the device-operand entry point against the host-operand one
+n = d.nbf_
+dC = [e.dev_put(x) for x in Cl]; dCr = [e.dev_put(x) for x in Cr]; dD = [e.dev_put(x @ y.T) for x, y in zip(Cl, Cr)]
+dJ = [e.dev_alloc(n * n * 8) for _ in Cl]; dK = [e.dev_alloc(n * n * 8) for _ in Cl]
+for rep in range(3):
+    e.compute_device(dC, dCr, [x.shape[1] for x in Cl], dD, dJ, dK, None)
+    got = [e.dev_get(p, (n, n)) for p in dJ + dK]
+    t = torch.tensor([float(np.frombuffer(g.tobytes(), dtype=np.uint64).sum() % (1 << 52)) for g in got], dtype=torch.float64, device="cuda")
+    lo, hi = t.clone(), t.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert torch.equal(lo, hi), "ranks hold different bits"
+    if rank == 0:
+        assert all(np.array_equal(a, b) for a, b in zip(J + K, got)), f"device arm differs from host arm (rep {rep})"
+print(f"RANK{rank} determinism_ok kind={st['reduce_kind']}", flush=True)
+e.close()
 dist.barrier(); dist.destroy_process_group()
 """
 
 
-def test_one_process_per_gpu_torchrun(tmp_path):
-    n = _ngpu()
-    if n < 2:
-        pytest.skip("needs >= 2 GPUs")
+@pytest.mark.parametrize("nproc", [2, 4, 8])
+@pytest.mark.parametrize("mode", ["p2p", "p2p_odd", "nccl"])
+def test_one_process_per_gpu_torchrun(tmp_path, nproc, mode):
+    """Parity against the oracle, worker ranks that bring nothing home, and bitwise determinism (run to run, rank to
+    rank, device-operand arm against host-operand arm) of the cross-GPU sum at 2 / 4 / 8 ranks."""
+    if _ngpu() < nproc:
+        pytest.skip(f"needs >= {nproc} GPUs")
     script = tmp_path / "rank.py"
     script.write_text(RANK_SCRIPT)
-    env = dict(os.environ, B2_ROOT=ROOT)
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 2)}",
-           "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)]
+    env = dict(os.environ, B2_ROOT=ROOT, B2_NBF="91" if mode == "p2p_odd" else "90")
+    if mode == "nccl":
+        env["B200JK_REDUCE"] = "nccl"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29611 + nproc), str(script)]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "RANK0 err=" in r.stdout and "RANK1 err=" in r.stdout
-    assert "RANK0 fetch_ok" in r.stdout and "RANK1 fetch_ok" in r.stdout
+    for k in range(nproc):
+        assert f"RANK{k} err=" in r.stdout and f"RANK{k} fetch_ok" in r.stdout and f"RANK{k} determinism_ok" in r.stdout
 
 
 LEGACY_SCRIPT = r"""
