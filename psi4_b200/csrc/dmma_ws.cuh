@@ -592,34 +592,47 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
             last = __shfl_sync(0xffffffffu, last, 0);  // ... before the warp is counted
             if (last) {
                 __threadfence();
-                // this warp's 32 x 64 part of the tile, summed over the splits in split order
+                // This warp's 32 x 64 part of the tile, summed over the splits in split order, one 8-row group at a
+                // time: the accumulators are dead by now, so four splits' worth of loads (32 x 16 bytes per lane) can be
+                // in flight at once -- with one split at a time this loop was latency-bound (~1.5 ms at the end of the
+                // kernel).  Dead edge columns of a partial tile hold zeros, so only the stores are predicated.
+                const double* src0 = p.ws + (size_t)tile * (BM * BN) + wn * 8 * NB + t * 2;
+                const size_t sstride = (size_t)p.ntiles * (BM * BN);
+#pragma unroll 1
+                for (int mb = 0; mb < mbv; mb++) {
+                    const int r = mb * 32 + wm * 8 + gq;
+                    const double* base = src0 + r * BN;
+                    double2 sum[NB];
 #pragma unroll
-                for (int a = 0; a < 4; a++)
+                    for (int nb = 0; nb < NB; nb++) sum[nb] = make_double2(0.0, 0.0);
+                    int sp = 0;
+#pragma unroll 1
+                    for (; sp + 4 <= p.nsplit; sp += 4) {
+                        double2 v[4][NB];
 #pragma unroll
-                    for (int b = 0; b < NB; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
-                for (int sp = 0; sp < p.nsplit; sp++) {
-                    const double* src = p.ws + ((size_t)sp * p.ntiles + tile) * (BM * BN);
+                        for (int u = 0; u < 4; u++)
 #pragma unroll
-                    for (int mb = 0; mb < 4; mb++) {
-                        if (mb < mbv) {
-                            const int r = mb * 32 + wm * 8 + gq;
+                            for (int nb = 0; nb < NB; nb++)
+                                v[u][nb] = __ldcg(reinterpret_cast<const double2*>(base + (size_t)(sp + u) * sstride + nb * 8));
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
 #pragma unroll
                             for (int nb = 0; nb < NB; nb++) {
-                                if (nb < nbv) {
-                                    const int c = wn * 8 * NB + nb * 8 + t * 2;
-                                    const double2 v = __ldcg(reinterpret_cast<const double2*>(src + r * BN + c));
-                                    acc[mb][nb][0] += v.x;
-                                    acc[mb][nb][1] += v.y;
-                                }
+                                sum[nb].x += v[u][nb].x;
+                                sum[nb].y += v[u][nb].y;
                             }
+                    }
+#pragma unroll 1
+                    for (; sp < p.nsplit; sp++) {
+#pragma unroll
+                        for (int nb = 0; nb < NB; nb++) {
+                            const double2 v = __ldcg(reinterpret_cast<const double2*>(base + (size_t)sp * sstride + nb * 8));
+                            sum[nb].x += v.x;
+                            sum[nb].y += v.y;
                         }
                     }
-                }
-#pragma unroll
-                for (int mb = 0; mb < 4; mb++) {
-                    const int r = mb * 32 + wm * 8 + gq;
                     const int m = tl.x * BM + r;
-                    if (mb < mbv && m < p.nbf) {
+                    if (m < p.nbf) {
 #pragma unroll
                         for (int nb = 0; nb < NB; nb++) {
 #pragma unroll
@@ -627,7 +640,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
                                 const int c = wn * 8 * NB + nb * 8 + t * 2 + e;
                                 const int n = tl.y * BN + c;
                                 if (nb < nbv && n < p.nbf && (!diag || c >= r)) {
-                                    const double v = acc[mb][nb][e];
+                                    const double v = e ? sum[nb].y : sum[nb].x;
                                     p.K[(size_t)m * p.nbf + n] += v;
                                     if (p.symmetric && n != m) p.K[(size_t)n * p.nbf + m] += v;
                                 }

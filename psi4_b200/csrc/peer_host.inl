@@ -267,13 +267,18 @@ int reduce_shards(b200jk* h, size_t off, size_t count, bool use_copy, int channe
             p.timeout_ns = peer_timeout_ns();
             p.status = s.peer.status;
             const size_t per = (count + W - 1) / W;
-            int grid = (int)std::min<size_t>(std::max<size_t>(1, (per / 2 + PR_THREADS - 1) / PR_THREADS), 64);
+            int grid = (int)std::min<size_t>(std::max<size_t>(1, (per / 2 + PR_THREADS - 1) / PR_THREADS), (size_t)s.nsm);
             Phase ph;
             ph.tag = 3;
             ph.a = get_event(s);
             ph.b = get_event(s);
             CK(cudaEventRecord(ph.a, st));
-            peer_reduce_kernel<<<grid, PR_THREADS, 0, st>>>(p);
+            switch (W) {
+                case 2: peer_reduce_kernel<2><<<grid, PR_THREADS, 0, st>>>(p); break;
+                case 4: peer_reduce_kernel<4><<<grid, PR_THREADS, 0, st>>>(p); break;
+                case 8: peer_reduce_kernel<8><<<grid, PR_THREADS, 0, st>>>(p); break;
+                default: peer_reduce_kernel<0><<<grid, PR_THREADS, 0, st>>>(p); break;
+            }
             s.launches++;
             CK(cudaGetLastError());
             CK(cudaEventRecord(ph.b, st));

@@ -77,6 +77,58 @@ __device__ __forceinline__ bool pr_wait(const unsigned* flag, unsigned epoch, un
     return true;
 }
 
+// element e (and e+1 when V == 2) of every window, summed in rank order; all W loads are issued before the first add
+template <int W, int V>
+__device__ __forceinline__ void pr_sum_store(const PeerReduceParams& p, int world, size_t e, bool to_host) {
+    double acc[V];
+    if constexpr (W > 0) {
+        double v[W][V];
+#pragma unroll
+        for (int r = 0; r < W; r++) {
+            if constexpr (V == 2) {
+                const double2 x = ld_peer2(p.win[r] + e);
+                v[r][0] = x.x;
+                v[r][1] = x.y;
+            } else {
+                v[r][0] = ld_peer1(p.win[r] + e);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < V; k++) acc[k] = v[0][k];
+#pragma unroll
+        for (int r = 1; r < W; r++)
+#pragma unroll
+            for (int k = 0; k < V; k++) acc[k] += v[r][k];
+    } else {  // any other world size: one load at a time
+#pragma unroll
+        for (int k = 0; k < V; k++) acc[k] = ld_peer1(p.win[0] + e + k);
+        for (int r = 1; r < world; r++)
+#pragma unroll
+            for (int k = 0; k < V; k++) acc[k] += ld_peer1(p.win[r] + e + k);
+    }
+    if (p.root < 0) {
+        for (int r = 0; r < world; r++) {
+            if constexpr (V == 2)
+                *reinterpret_cast<double2*>(p.win[r] + e) = make_double2(acc[0], acc[1]);
+            else
+                p.win[r][e] = acc[0];
+        }
+    } else {
+        if constexpr (V == 2)
+            *reinterpret_cast<double2*>(p.win[p.root] + e) = make_double2(acc[0], acc[1]);
+        else
+            p.win[p.root][e] = acc[0];
+    }
+    if (to_host) {
+        if constexpr (V == 2)
+            *reinterpret_cast<double2*>(p.host_dst + e) = make_double2(acc[0], acc[1]);
+        else
+            p.host_dst[e] = acc[0];
+    }
+}
+
+// W = compile-time world size (2, 4, 8: fully unrolled loads) or 0 (run-time loop)
+template <int W>
 __global__ void __launch_bounds__(PR_THREADS) peer_reduce_kernel(PeerReduceParams p) {
     unsigned* myf = p.flags[p.rank];
     __shared__ int s_last;
@@ -96,45 +148,13 @@ __global__ void __launch_bounds__(PR_THREADS) peer_reduce_kernel(PeerReduceParam
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     if (((p.off + a) & 1) == 0) {
         const size_t n2 = (b - a) >> 1;
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < n2; i += stride) {
-            const size_t e = p.off + a + 2 * i;
-            double2 acc = ld_peer2(p.win[0] + e);
-#pragma unroll 1
-            for (int r = 1; r < p.world; r++) {
-                const double2 v = ld_peer2(p.win[r] + e);
-                acc.x += v.x;
-                acc.y += v.y;
-            }
-            if (p.root < 0) {
-                for (int r = 0; r < p.world; r++) *reinterpret_cast<double2*>(p.win[r] + e) = acc;
-            } else {
-                *reinterpret_cast<double2*>(p.win[p.root] + e) = acc;
-            }
-            if (to_host) *reinterpret_cast<double2*>(p.host_dst + e) = acc;
-        }
-        if (((b - a) & 1) && blockIdx.x == 0 && tid == 0) {  // odd tail (last slice of an odd count)
-            const size_t e = p.off + b - 1;
-            double acc = ld_peer1(p.win[0] + e);
-            for (int r = 1; r < p.world; r++) acc += ld_peer1(p.win[r] + e);
-            if (p.root < 0) {
-                for (int r = 0; r < p.world; r++) p.win[r][e] = acc;
-            } else {
-                p.win[p.root][e] = acc;
-            }
-            if (to_host) p.host_dst[e] = acc;
-        }
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < n2; i += stride)
+            pr_sum_store<W, 2>(p, p.world, p.off + a + 2 * i, to_host);
+        if (((b - a) & 1) && blockIdx.x == 0 && tid == 0)  // odd tail (last slice of an odd count)
+            pr_sum_store<W, 1>(p, p.world, p.off + b - 1, to_host);
     } else {
-        for (size_t i = a + (size_t)blockIdx.x * blockDim.x + tid; i < b; i += stride) {
-            const size_t e = p.off + i;
-            double acc = ld_peer1(p.win[0] + e);
-            for (int r = 1; r < p.world; r++) acc += ld_peer1(p.win[r] + e);
-            if (p.root < 0) {
-                for (int r = 0; r < p.world; r++) p.win[r][e] = acc;
-            } else {
-                p.win[p.root][e] = acc;
-            }
-            if (to_host) p.host_dst[e] = acc;
-        }
+        for (size_t i = a + (size_t)blockIdx.x * blockDim.x + tid; i < b; i += stride)
+            pr_sum_store<W, 1>(p, p.world, p.off + i, to_host);
     }
 
     // ---- barrier B: the last CTA of this rank speaks for all of them ----

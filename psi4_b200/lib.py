@@ -179,8 +179,8 @@ class Engine:
         """Unfitted symmetric-packed rows [m0, m1) -> fitted, mirrored rows of tensor `which` (on the device)."""
         p = np.ascontiguousarray(sym_rows, dtype=np.float64)
         need = int(self._symm_big_skips[m1] - self._symm_big_skips[m0])
-        if p.size != need:
-            raise B200JKError(1, f"symmetric-packed block has {p.size} doubles, layout says {need}")
+        if p.size < need:  # psi4 hands over one reused block buffer sized for its largest block (dfhelper.cc:553-585)
+            raise B200JKError(1, f"symmetric-packed block has {p.size} doubles, layout needs {need}")
         self._check(self.L.b200jk_fit_rows(self.h, which, m0, m1, _d(p)))
 
     def fit_stats(self) -> dict:
