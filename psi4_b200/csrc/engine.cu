@@ -122,9 +122,15 @@ struct Shard {
     // (buffer, rows, box rows): in an SCF nocc never changes, so the maps are encoded once
     double* Cg = nullptr;
     size_t cg_cap = 0;
-    CUtensorMap* d_cgmaps = nullptr;
-    const double* cg_key_ptr = nullptr;
-    int cg_key_rows = 0, cg_key_box = 0;
+    // a few map sets, each keyed on (buffer, rows, box rows): an open-shell build alternates between two occupied
+    // counts (n_alpha != n_beta) and must not re-encode nbf maps -- and drain the stream -- twice per iteration
+    struct CgMaps {
+        CUtensorMap* d = nullptr;
+        const double* ptr = nullptr;
+        int rows = 0, box = 0;
+        uint64_t used = 0;
+    } cgmaps[4];
+    uint64_t cg_clock = 0;
     bool screened = false;  // some row-block keeps fewer than nbf partners
     char* fit_meta[2] = {nullptr, nullptr};  // page-locked index tables of a group (see fit_group)
     size_t fit_meta_cap[2] = {0, 0};
@@ -150,6 +156,7 @@ struct Shard {
     uint64_t launches = 0;
     // half transforms skipped in the current build because C_left repeated (Task::same_left): sum of q rows, q rows x nocc
     double skipped_q = 0, skipped_qo = 0;
+    int j_reads = 0;  // passes over the tensor the J sweeps of the current build made (first sweeps + batched second sweeps)
 };
 }  // namespace
 
@@ -419,21 +426,29 @@ int run_half_ws(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o
             Ct, ldc, o, fj ? fj->Dm : nullptr, fj ? fj->ldd : 0, s.d_sp, s.d_ldm, s.d_row_off_unit, s.d_cols, s.d_cols_off, s.Cg);
         s.launches++;
         CK(cudaGetLastError());
-        if (!s.d_cgmaps || s.cg_key_ptr != s.Cg || s.cg_key_rows != R || s.cg_key_box != 16 * NB) {
+        Shard::CgMaps* hit = nullptr;
+        Shard::CgMaps* victim = &s.cgmaps[0];
+        for (auto& c : s.cgmaps) {
+            if (c.d && c.ptr == s.Cg && c.rows == R && c.box == 16 * NB) hit = &c;
+            if (c.used < victim->used) victim = &c;
+        }
+        if (!hit) {
+            hit = victim;
             std::vector<CUtensorMap> maps(h->nbf);
             for (size_t m = 0; m < h->nbf; m++)
                 if ((rc = make_map(h, &maps[m], s.Cg + h->row_off_unit[m] * (size_t)R, (uint64_t)h->sp[m], (uint64_t)R,
                                    (uint64_t)h->ldm[m] * 8, (uint32_t)(16 * NB))))
                     return rc;
-            if (!s.d_cgmaps) CK(cudaMalloc((void**)&s.d_cgmaps, h->nbf * sizeof(CUtensorMap)));
+            if (!hit->d) CK(cudaMalloc((void**)&hit->d, h->nbf * sizeof(CUtensorMap)));
             // (pageable source: the copy is staged before the call returns, and it is stream-ordered before K3)
-            CK(cudaMemcpyAsync(s.d_cgmaps, maps.data(), h->nbf * sizeof(CUtensorMap), cudaMemcpyHostToDevice, s.stream));
+            CK(cudaMemcpyAsync(hit->d, maps.data(), h->nbf * sizeof(CUtensorMap), cudaMemcpyHostToDevice, s.stream));
             CK(cudaStreamSynchronize(s.stream));
-            s.cg_key_ptr = s.Cg;
-            s.cg_key_rows = R;
-            s.cg_key_box = 16 * NB;
+            hit->ptr = s.Cg;
+            hit->rows = R;
+            hit->box = 16 * NB;
         }
-        cgmaps = s.d_cgmaps;
+        hit->used = ++s.cg_clock;
+        cgmaps = hit->d;
     }
     CUtensorMap ctmap, ctmap_last, dmap;
     int rc = make_map(h, &ctmap, Ct, h->nbf, (uint64_t)o, (uint64_t)ldc * 8, (uint32_t)(16 * NB));
@@ -625,8 +640,22 @@ int run_kgemm(b200jk* h, Shard& s, const double* T1, const double* T2, int kdim,
     return 0;
 }
 
-// J sweeps of one density.  first_sweep_done: d_part was already produced by the fused half transform.
-int run_j(b200jk* h, Shard& s, const double* D, bool symmetric, double* Jout, double* dpart, bool first_sweep_done) {
+// J sweeps of one shard: per density the first sweep (unless the fused half transform already produced d_part) and
+// the fixed-order reduction to d[q]; then the second sweep for up to J_MAX_ND densities per pass over the tensor.
+template <int ND>
+int launch_j_mn(b200jk* h, Shard& s, const JParams& p, const JBatch& bt) {
+    static bool attr_set[64] = {false};
+    if (!attr_set[s.dev]) {
+        CK(cudaFuncSetAttribute(j_mn_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set[s.dev] = true;
+    }
+    j_mn_kernel<ND><<<dim3((h->max_sp + 127) / 128, (unsigned)h->nbf), J_THREADS, (size_t)ND * s.nq * sizeof(double), s.stream>>>(p, bt);
+    s.launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int run_j_all(b200jk* h, Shard& s, int nmat, const double* const* D, bool symmetric, double* Jout0, size_t n2) {
     if (s.nq == 0) return 0;  // an empty Q shard (naux < number of GPUs) contributes the zeros of the memset
     JParams p;
     p.tensor = s.tensor[B200JK_TENSOR_PPQ];
@@ -639,32 +668,50 @@ int run_j(b200jk* h, Shard& s, const double* D, bool symmetric, double* Jout, do
     p.nbf = (int)h->nbf;
     p.nq = s.nq;
     p.symmetric = symmetric ? 1 : 0;
-    p.D = D;
-    p.dpart = dpart;
-    p.d = s.dvec;
-    p.J = Jout;
+    p.J = nullptr;
     static bool attr_set[64] = {false};
     if (!attr_set[s.dev]) {
         CK(cudaFuncSetAttribute(j_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CK(cudaFuncSetAttribute(j_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set[s.dev] = true;
     }
-    size_t sm1 = (size_t)(h->max_sp + 2) * sizeof(double);
-    size_t sm2 = (size_t)s.nq * sizeof(double);
-    if (sm1 > 200 * 1024 || sm2 > 200 * 1024)
+    const size_t sm1 = (size_t)(h->max_sp + 2) * sizeof(double);
+    const size_t smq = (size_t)s.nq * sizeof(double);
+    if (sm1 > 200 * 1024 || smq > 200 * 1024)
         return fail(h, B200JK_ERR_INVALID, "J kernels: nbf %d / shard naux %d exceed the shared-memory staging limit",
                     h->max_sp, s.nq);
-    if (!first_sweep_done) {
-        j_dq_kernel<<<dim3((s.nq + J1_ROWS - 1) / J1_ROWS, (unsigned)h->nbf), J_THREADS, sm1, s.stream>>>(p);
+    s.j_reads = 0;
+    for (int i = 0; i < nmat; i++) {
+        p.D = D[i];
+        p.dpart = s.dpart + (size_t)i * h->nbf * (size_t)s.nq;
+        p.d = s.dvec + (size_t)i * s.nq;
+        if (!s.fused[i]) {
+            j_dq_kernel<<<dim3((s.nq + J1_ROWS - 1) / J1_ROWS, (unsigned)h->nbf), J_THREADS, sm1, s.stream>>>(p);
+            s.j_reads++;
+            s.launches++;
+            CK(cudaGetLastError());
+        }
+        j_dq_reduce_kernel<<<(s.nq + JR_Q - 1) / JR_Q, JR_Q * JR_M, 0, s.stream>>>(p.dpart, p.nbf, s.nq, p.d);
         s.launches++;
         CK(cudaGetLastError());
     }
-    j_dq_reduce_kernel<<<(s.nq + JR_Q - 1) / JR_Q, JR_Q * JR_M, 0, s.stream>>>(dpart, p.nbf, s.nq, s.dvec);
-    s.launches++;
-    CK(cudaGetLastError());
-    j_mn_kernel<<<dim3((h->max_sp + 127) / 128, (unsigned)h->nbf), J_THREADS, sm2, s.stream>>>(p);
-    s.launches++;
-    CK(cudaGetLastError());
+    const int nd_max = (int)std::max<size_t>(1, std::min<size_t>(J_MAX_ND, (200 * 1024) / smq));
+    for (int i0 = 0; i0 < nmat; i0 += nd_max) {
+        const int nd = std::min(nd_max, nmat - i0);
+        JBatch bt;
+        for (int k = 0; k < J_MAX_ND; k++) {
+            bt.d[k] = s.dvec + (size_t)(i0 + std::min(k, nd - 1)) * s.nq;
+            bt.J[k] = Jout0 + (size_t)(i0 + std::min(k, nd - 1)) * n2;
+        }
+        int rc;
+        switch (nd) {
+            case 1: rc = launch_j_mn<1>(h, s, p, bt); break;
+            case 2: rc = launch_j_mn<2>(h, s, p, bt); break;
+            case 3: rc = launch_j_mn<3>(h, s, p, bt); break;
+            default: rc = launch_j_mn<4>(h, s, p, bt); break;
+        }
+        if (rc) return rc;
+        s.j_reads++;
+    }
     return 0;
 }
 
@@ -704,8 +751,8 @@ int ensure_work(b200jk* h, Shard& s, const Task& t, int* qc_out) {
         if ((rc = grow(h, &s.out, &s.out_cap, need))) return rc;
     }
     if (t.do_J) {
-        // one d_part per density: the fused half transforms of all densities run before the J sweeps
-        if ((rc = grow(h, &s.dpart, &s.dpart_cap, (size_t)t.nmat * N * (size_t)s.nq + (size_t)s.nq))) return rc;
+        // one d_part (and one d) per density: the fused half transforms of all densities run before the J sweeps
+        if ((rc = grow(h, &s.dpart, &s.dpart_cap, (size_t)t.nmat * (N + 1) * (size_t)s.nq))) return rc;
         s.dvec = s.dpart + (size_t)t.nmat * N * (size_t)s.nq;
         if (t.do_K && (rc = grow(h, &s.Dm, &s.dm_cap, (size_t)t.nmat * N * (size_t)round_up((int)N, 2)))) return rc;
     }
@@ -786,13 +833,8 @@ int run_device_J(b200jk* h, Shard& s, const Task& t, const double* const* dD) {
     CK(cudaSetDevice(s.dev));
     const OutLayout ol = out_layout(t);
     CK(cudaMemsetAsync(s.out + ol.offJ, 0, ol.countJ * sizeof(double), s.stream));
-    int rc;
     PhaseScope ps(s, 0);
-    for (int i = 0; i < t.nmat; i++)
-        if ((rc = run_j(h, s, dD[i], t.lr, s.out + ol.offJ + i * t.n2, s.dpart + (size_t)i * h->nbf * (size_t)s.nq,
-                        s.fused[i] != 0)))
-            return rc;
-    return 0;
+    return run_j_all(h, s, t.nmat, dD, t.lr, s.out + ol.offJ, t.n2);
 }
 
 // The K and wK builds of one shard (K3, K4 per density and Q chunk).  When J is tasked too (dD != nullptr) the first
@@ -883,10 +925,10 @@ void account_work(b200jk* h, const Task& t) {
     double Aloc = 0;
     for (auto& s : h->sh) Aloc += s.nq;
     st.j_bytes = st.half_flops = st.half_bytes = st.kgemm_flops = 0;
+    // J traffic = the passes over the tensor the sweeps actually make: a fused first sweep rides on the half
+    // transform's read, and one second sweep serves up to J_MAX_ND densities (never credit bytes that were not read)
+    if (t.do_J && !h->sh.empty()) st.j_bytes = (double)h->sh[0].j_reads * 8.0 * Aloc * (t.lr ? Ptri : P);
     for (int i = 0; i < t.nmat; i++) {
-        // a fused first sweep rides on the half transform's read of the tensor: only the second sweep is J traffic
-        const bool fused = !h->sh.empty() && (int)h->sh[0].fused.size() > i && h->sh[0].fused[i];
-        if (t.do_J) st.j_bytes += (fused ? 1.0 : 2.0) * 8.0 * Aloc * (t.lr ? Ptri : P);
         double o = t.nocc[i];
         if (o == 0) continue;
         if (t.do_K) {
@@ -1055,7 +1097,9 @@ void free_shard(Shard& s) {
         if (s.tensor[w]) cudaFree(s.tensor[w]);
         if (s.d_amaps[w]) cudaFree(s.d_amaps[w]);
     }
-    void* ptrs[] = {s.Cg, s.d_cgmaps, s.d_row_off_unit, s.d_counter, s.d_tiles_sym, s.d_tiles_full, s.d_mpos, s.d_metric, s.fit_raw[0], s.fit_raw[1], s.fit_t, s.Dm,
+    for (auto& c : s.cgmaps)
+        if (c.d) cudaFree(c.d);
+    void* ptrs[] = {s.Cg, s.d_row_off_unit, s.d_counter, s.d_tiles_sym, s.d_tiles_full, s.d_mpos, s.d_metric, s.fit_raw[0], s.fit_raw[1], s.fit_t, s.Dm,
                     s.d_fit_dst_off, s.d_fit_src_off, s.d_fit_dst_ld, s.d_fit_mi, s.d_fit_j0, s.d_fit_m,
                     s.d_row_off, s.d_ldm, s.d_sp, s.d_ign, s.d_cols, s.d_cols_off, s.in, s.out,
                     s.Ctl,       s.Ctr,   s.dpart, s.T1,  s.T2,     s.ws};
@@ -1232,9 +1276,10 @@ int b200jk_set_layout(b200jk_t* h, size_t nbf, size_t naux, const size_t* small_
             s.tensor[w] = nullptr;
             s.d_amaps[w] = nullptr;
         }
-        if (s.d_cgmaps) CK(cudaFree(s.d_cgmaps));
-        s.d_cgmaps = nullptr;
-        s.cg_key_ptr = nullptr;
+        for (auto& c : s.cgmaps) {
+            if (c.d) CK(cudaFree(c.d));
+            c = Shard::CgMaps();
+        }
         if (s.d_metric) CK(cudaFree(s.d_metric));
         s.d_metric = nullptr;
         s.have_metric = false;

@@ -132,54 +132,80 @@ __global__ void j_prep_dm_kernel(const double* __restrict__ D, int nbf, int ldd,
 // K2.  grid = (ceil(max_sp/128), nbf).  CTA: row-block m, packed columns [kt*128, kt*128+128).
 // Warp w sums rows q = w, w+8, ...; lane owns columns 2*lane,+1 and 64+2*lane,+1.  Cross-warp
 // reduction in shared memory in fixed order, then the sparse->dense unpack writes J directly.
-__global__ void __launch_bounds__(J_THREADS) j_mn_kernel(JParams p) {
+// ND densities ride on ONE read of the tensor (UHF passes two, response builds several: the reference re-reads B
+// per density, dfhelper.cc:3177 loops over i): d vectors side by side in shared memory, ND accumulator sets per lane;
+// per density the arithmetic is exactly the ND = 1 kernel's.
+constexpr int J_MAX_ND = 4;
+struct JBatch {
+    const double* d[J_MAX_ND];  // [nq] each
+    double* J[J_MAX_ND];        // [nbf][nbf] each
+};
+template <int ND>
+__global__ void __launch_bounds__(J_THREADS) j_mn_kernel(JParams p, JBatch bt) {
     __shared__ double red[8][128];
-    extern __shared__ __align__(16) double dq[];  // d[q] staged once per CTA
+    extern __shared__ __align__(16) double dq[];  // d[dens][q] staged once per CTA
     const int m = blockIdx.y;
     const int sp = p.sp[m];
     const int kt0 = blockIdx.x * 128;
     if (kt0 >= sp) return;
     const int kstart = p.symmetric ? p.ign[m] : 0;
     if (kt0 + 128 <= kstart) return;
-    for (int q = threadIdx.x; q < p.nq; q += blockDim.x) dq[q] = p.d[q];
+#pragma unroll
+    for (int dn = 0; dn < ND; dn++)
+        for (int q = threadIdx.x; q < p.nq; q += blockDim.x) dq[dn * p.nq + q] = bt.d[dn][q];
     __syncthreads();
     const int ldm = p.ldm[m];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double* Bm = p.tensor + p.row_off[m];
     const int ka = kt0 + lane * 2, kb = ka + 64;
     const bool va = ka < ldm, vb = kb < ldm;  // ldm is a multiple of 4: ka+1 < ldm when ka < ldm
-    double a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+    double a0[ND], a1[ND], b0[ND], b1[ND];
+#pragma unroll
+    for (int dn = 0; dn < ND; dn++) a0[dn] = a1[dn] = b0[dn] = b1[dn] = 0.0;
     const double* base = Bm + (size_t)warp * ldm;
     const size_t step = (size_t)8 * ldm;
     int q = warp;
 #pragma unroll 4
     for (; q < p.nq; q += 8, base += step) {
-        double w = dq[q];
+        double w[ND];
+#pragma unroll
+        for (int dn = 0; dn < ND; dn++) w[dn] = dq[dn * p.nq + q];
         if (va) {
             double2 x = __ldcs(reinterpret_cast<const double2*>(base + ka));
-            a0 = fma(x.x, w, a0);
-            a1 = fma(x.y, w, a1);
+#pragma unroll
+            for (int dn = 0; dn < ND; dn++) {
+                a0[dn] = fma(x.x, w[dn], a0[dn]);
+                a1[dn] = fma(x.y, w[dn], a1[dn]);
+            }
         }
         if (vb) {
             double2 y = __ldcs(reinterpret_cast<const double2*>(base + kb));
-            b0 = fma(y.x, w, b0);
-            b1 = fma(y.y, w, b1);
+#pragma unroll
+            for (int dn = 0; dn < ND; dn++) {
+                b0[dn] = fma(y.x, w[dn], b0[dn]);
+                b1[dn] = fma(y.y, w[dn], b1[dn]);
+            }
         }
     }
-    red[warp][lane * 2] = a0;
-    red[warp][lane * 2 + 1] = a1;
-    red[warp][64 + lane * 2] = b0;
-    red[warp][64 + lane * 2 + 1] = b1;
-    __syncthreads();
-    if (threadIdx.x < 128) {
-        int k = kt0 + threadIdx.x;
-        if (k < sp && k >= kstart) {
-            double s = 0.0;
 #pragma unroll
-            for (int w = 0; w < 8; w++) s += red[w][threadIdx.x];
-            int n = p.cols[p.cols_off[m] + k];
-            p.J[(size_t)m * p.nbf + n] += s;
-            if (p.symmetric && n != m) p.J[(size_t)n * p.nbf + m] += s;
+    for (int dn = 0; dn < ND; dn++) {
+        if (dn) __syncthreads();
+        red[warp][lane * 2] = a0[dn];
+        red[warp][lane * 2 + 1] = a1[dn];
+        red[warp][64 + lane * 2] = b0[dn];
+        red[warp][64 + lane * 2 + 1] = b1[dn];
+        __syncthreads();
+        if (threadIdx.x < 128) {
+            int k = kt0 + threadIdx.x;
+            if (k < sp && k >= kstart) {
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; w++) s += red[w][threadIdx.x];
+                int n = p.cols[p.cols_off[m] + k];
+                double* J = bt.J[dn];
+                J[(size_t)m * p.nbf + n] += s;
+                if (p.symmetric && n != m) J[(size_t)n * p.nbf + m] += s;
+            }
         }
     }
 }
