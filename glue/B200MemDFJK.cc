@@ -29,8 +29,11 @@ void B200DFHelper::move_to_device(b200jk_t* h, bool release_host) {
         // analogue is more Q shards, so refuse instead of degrading (SCF_SUBTYPE=INCORE semantics, :259-262)
         throw PSIEXCEPTION("B200MemDFJK: DFHelper chose the out-of-core algorithm; set SCF_SUBTYPE INCORE / raise memory");
     }
+    // (a second initialize() on the same object lands here again: set_layout re-initialises the engine, which drops the
+    // tensors of the previous pass, and the fresh ones go up -- MemDFJK::preiterations simply recomputes, so do we)
     check(h, b200jk_set_layout(h, nbf_, naux_, small_skips_.data(), big_skips_.data(), schwarz_fun_index_.data()),
           "set_layout");
+    layout_sent_ = true;
     // pageable memory is fine here: the engine copies it through its page-locked ring with a few threads while the
     // DMA engines drain it (measured 16-32 GB/s on the B200 box; page-locking the whole tensor first costs more than
     // it saves for a one-shot upload)
@@ -49,8 +52,11 @@ void B200DFHelper::move_to_device(b200jk_t* h, bool release_host) {
 
 size_t B200DFHelper::device_bytes_per_gpu(b200jk_t* h, size_t max_nocc) {
     if (!sparsity_prepared_) prepare_sparsity();
-    check(h, b200jk_set_layout(h, nbf_, naux_, small_skips_.data(), big_skips_.data(), schwarz_fun_index_.data()),
-          "set_layout");
+    if (!layout_sent_) {  // after move_to_device the engine already has the tables (and the tensors that hang on them)
+        check(h, b200jk_set_layout(h, nbf_, naux_, small_skips_.data(), big_skips_.data(), schwarz_fun_index_.data()),
+              "set_layout");
+        layout_sent_ = true;
+    }
     uint64_t bytes = 0;
     check(h, b200jk_hbm_estimate(h, max_nocc, do_wK_ ? 1 : 0, &bytes), "hbm_estimate");
     return static_cast<size_t>(bytes);
@@ -63,11 +69,34 @@ B200MemDFJK::B200MemDFJK(std::shared_ptr<BasisSet> primary, std::shared_ptr<Basi
     : MemDFJK(primary, auxiliary, options), ngpu_(ngpu), release_host_(release_host) {
     // common_init (MemDFJK.cc:64) made a plain DFHelper; swap in the subclass that can reach the tables
     dfh_ = std::make_shared<B200DFHelper>(primary, auxiliary);
-    check(nullptr, b200jk_create(&handle_, ngpu_, nullptr), "create");
+    int rc = b200jk_create(&handle_, ngpu_, nullptr);
+    if (rc != B200JK_OK) {
+        // the handle exists even when creation failed half-way (it carries the message); the destructor will not run
+        std::string msg = std::string("B200MemDFJK: create: ") + b200jk_last_error(handle_);
+        if (handle_) b200jk_destroy(handle_);
+        handle_ = nullptr;
+        throw PSIEXCEPTION(msg);
+    }
+}
+
+std::shared_ptr<B200MemDFJK> B200MemDFJK::build(std::shared_ptr<BasisSet> primary, std::shared_ptr<BasisSet> auxiliary,
+                                                Options& options, int ngpu, bool release_host) {
+    auto jk = std::make_shared<B200MemDFJK>(primary, auxiliary, options, ngpu, release_host);
+    jk->set_wcombine(false);  // jk.cc:145-146
+    // _set_dfjk_options<MemDFJK>, jk.cc:58-68
+    double cutoff = options.get_str("SCREENING") == "NONE" ? 0.0 : options.get_double("INTS_TOLERANCE");
+    if (options["INTS_TOLERANCE"].has_changed() || options.get_str("SCREENING") == "NONE") jk->set_cutoff(cutoff);
+    if (options["PRINT"].has_changed()) jk->set_print(options.get_int("PRINT"));
+    if (options["DEBUG"].has_changed()) jk->set_debug(options.get_int("DEBUG"));
+    if (options["BENCH"].has_changed()) jk->set_bench(options.get_int("BENCH"));
+    jk->set_condition(options.get_double("DF_FITTING_CONDITION"));
+    if (options["DF_INTS_NUM_THREADS"].has_changed()) jk->set_df_ints_num_threads(options.get_int("DF_INTS_NUM_THREADS"));
+    if (options["WCOMBINE"].has_changed()) jk->set_wcombine(options.get_bool("WCOMBINE"));  // jk.cc:148
+    return jk;
 }
 
 B200MemDFJK::~B200MemDFJK() {
-    if (handle_) b200jk_destroy(handle_);  // also unregisters any page-locked matrices
+    if (handle_) b200jk_destroy(handle_);  // also unregisters the page-locked matrices (pinned_ still holds them)
 }
 
 void B200MemDFJK::fail(const std::string& where) const {
@@ -82,15 +111,16 @@ void B200MemDFJK::preiterations() {
 }
 
 void B200MemDFJK::register_persistent_matrices() {
-    // D_ao_/J_ao_/K_ao_/wK_ao_ are allocated once by JK::allocate_JK / USO2AO (jk.cc:355-446) and reused by every
-    // compute(); page-locking them lets the engine DMA in place.  When the matrix count changes psi4 re-allocates
-    // them, so the set of pointers is compared on every build: vanished ones are unregistered, new ones registered
-    // (anything left unregistered is simply staged through the engine's pinned buffers).
+    // D_ao_/J_ao_/K_ao_/wK_ao_ are allocated once by JK::compute_D / allocate_JK / USO2AO (jk.cc:314-446) and reused by
+    // every compute(); page-locking them lets the engine DMA in place.  When the matrix count changes psi4 re-creates
+    // them, so the set is compared on every build: matrices psi4 no longer uses are unregistered FIRST and only then
+    // released (the glue's reference kept them alive, so the memory was never freed while page-locked), new ones
+    // are registered.  Anything that cannot be registered is simply staged through the engine's pinned buffers.
     // (sizes from the matrices themselves: basisset.h pulls in <libint2/shell.h>, which this file does not need)
-    std::vector<std::pair<double*, size_t>> now;
+    std::vector<SharedMatrix> now;
     auto collect = [&](std::vector<SharedMatrix>& v) {
         for (auto& m : v)
-            if (m) now.push_back({m->get_pointer(), sizeof(double) * m->rowspi()[0] * m->colspi()[0]});
+            if (m) now.push_back(m);
     };
     collect(D_ao_);
     if (do_J_) collect(J_ao_);
@@ -100,11 +130,15 @@ void B200MemDFJK::register_persistent_matrices() {
     for (auto& old : pinned_) {
         bool keep = false;
         for (auto& n : now) keep = keep || n == old;
-        if (!keep) b200jk_unregister_host(handle_, old.first);  // already freed by psi4: best effort
+        if (!keep && b200jk_unregister_host(handle_, old->get_pointer()) != B200JK_OK) fail("unregister_host");
     }
-    for (auto& n : now)
-        if (b200jk_register_host(handle_, n.first, n.second) != B200JK_OK) fail("register_host");
-    pinned_ = now;
+    for (auto& n : now) {
+        bool have = false;
+        for (auto& old : pinned_) have = have || n == old;
+        const size_t bytes = sizeof(double) * n->rowspi()[0] * n->colspi()[0];
+        if (!have && bytes && b200jk_register_host(handle_, n->get_pointer(), bytes) != B200JK_OK) fail("register_host");
+    }
+    pinned_ = now;  // drops the last reference to the matrices psi4 has already let go of
 }
 
 void B200MemDFJK::compute_JK() {

@@ -38,6 +38,9 @@ class B200DFHelper : public DFHelper {
     size_t device_bytes_per_gpu(b200jk_t* h, size_t max_nocc);
 
     bool tensors_on_host() const { return static_cast<bool>(Ppq_); }
+
+   private:
+    bool layout_sent_ = false;  // the engine holds this object's tables (a second set_layout would drop the tensors)
 };
 
 class B200MemDFJK : public MemDFJK {
@@ -45,7 +48,10 @@ class B200MemDFJK : public MemDFJK {
     b200jk_t* handle_ = nullptr;
     int ngpu_;
     bool release_host_;
-    std::vector<std::pair<double*, size_t>> pinned_;  // page-locked D/J/K/wK matrices
+    // page-locked D/J/K/wK matrices.  The glue holds a reference to each while it is registered: psi4 re-creates the
+    // matrices whenever the matrix count changes (JK::compute_D / allocate_JK, jk.cc:314-389), and memory must not go
+    // back to the allocator while it is still cudaHostRegister'ed.
+    std::vector<SharedMatrix> pinned_;
 
     std::string name() override { return "B200MemDFJK"; }
     void preiterations() override;   // MemDFJK.cc:71-96, then upload
@@ -60,6 +66,16 @@ class B200MemDFJK : public MemDFJK {
     B200MemDFJK(std::shared_ptr<BasisSet> primary, std::shared_ptr<BasisSet> auxiliary, Options& options,
                 int ngpu = 1, bool release_host = true);
     ~B200MemDFJK() override;
+
+    /// What JK::build_JK does for SCF_TYPE = MEM_DF (libfock/jk.cc:143-148) with this class in MemDFJK's place:
+    /// construct, set_wcombine(false), then _set_dfjk_options (jk.cc:58-68: DF_FITTING_CONDITION, INTS_TOLERANCE /
+    /// SCREENING, PRINT, DEBUG, BENCH, DF_INTS_NUM_THREADS) and WCOMBINE.  Both attach points of INTEGRATION.md use
+    /// it, so a B200MemDFJK is configured exactly as the stock MemDFJK of the same options would be.
+    static std::shared_ptr<B200MemDFJK> build(std::shared_ptr<BasisSet> primary, std::shared_ptr<BasisSet> auxiliary,
+                                              Options& options, int ngpu = 1, bool release_host = true);
+
+    double condition() const { return condition_; }
+    size_t pinned_matrices() const { return pinned_.size(); }
 
     void print_header() const override;
 

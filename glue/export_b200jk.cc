@@ -20,7 +20,8 @@ PYBIND11_MODULE(b200jk_psi4, m) {
     py::module_::import("psi4.core");  // registers JK / MemDFJK / BasisSet first
     py::class_<B200MemDFJK, std::shared_ptr<B200MemDFJK>, MemDFJK>(m, "B200MemDFJK", "MEM_DF J/K on B200 GPUs")
         .def(py::init([](std::shared_ptr<BasisSet> primary, std::shared_ptr<BasisSet> aux, int ngpu, bool release_host) {
-                 return std::make_shared<B200MemDFJK>(primary, aux, Process::environment.options, ngpu, release_host);
+                 // configured like JK::build_JK configures a MEM_DF object (jk.cc:143-148, _set_dfjk_options :58-68)
+                 return B200MemDFJK::build(primary, aux, Process::environment.options, ngpu, release_host);
              }),
              py::arg("primary"), py::arg("auxiliary"), py::arg("ngpu") = 1, py::arg("release_host") = true)
         .def("last_stats", [](const B200MemDFJK& jk) {

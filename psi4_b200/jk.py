@@ -177,7 +177,8 @@ class MemDFJK(JK):
     """
 
     def __init__(self, dfh: DFHelper, Ppq=None, m1Ppq=None, wPpq=None, *, ngpu: int = 1, devices=None,
-                 rank=None, world=None, device=None, nccl_id=None, synthetic=None, unfitted=None):
+                 rank=None, world=None, device=None, nccl_id=None, synthetic=None, unfitted=None, provider=None,
+                 fit_block: int = 64):
         super().__init__(dfh.nbf_)
         if not dfh.sparsity_prepared_:
             raise PsiException("MemDFJK: DFHelper sparsity not prepared")
@@ -185,7 +186,16 @@ class MemDFJK(JK):
         self.condition_ = 1.0e-12  # jk.h:1142
         self._Ppq, self._m1Ppq, self._wPpq = Ppq, m1Ppq, wPpq
         self._synthetic = synthetic  # (seed, amp) -> device-side fill, bench / large tests only
-        self._unfitted = unfitted    # (symmetric-packed unfitted (A|mn), metric power, rows per block) -> fit on device
+        # unfitted: tensor id -> (symmetric-packed unfitted integrals, metric power or None) -> fitted on the device;
+        # the older triple (sym, metric, rows per block) for the Ppq tensor alone is still understood
+        if unfitted is not None and not isinstance(unfitted, dict):
+            sym, metric, fit_block = unfitted
+            unfitted = {_lib.TENSOR_PPQ: (sym, metric)}
+        self._unfitted = unfitted
+        self._fit_block = int(fit_block)
+        # provider(cutoff, condition, omega, do_wK) -> the host part of DFHelper::initialize (scf.DFTensors), run by
+        # preiterations() with the knob values current THEN (MemDFJK.cc:71-96), not with those of construction time
+        self._provider = provider
         self._engine_args = dict(ngpu=ngpu, devices=devices, rank=rank, world=world, device=device, nccl_id=nccl_id)
         self.engine: _lib.Engine | None = None
 
@@ -208,6 +218,13 @@ class MemDFJK(JK):
         """MemDFJK.cc:71-96: configure, then move the in-core tensors into HBM (Q-sharded)."""
         if self.engine is not None:
             return
+        if self._provider is not None:
+            if self.do_wK_ and not self.omega_ > 0.0:
+                raise PsiException("MemDFJK: wK tasked but omega is not set (JK::set_omega)")
+            t = self._provider(self.cutoff_, self.condition_, self.omega_, self.do_wK_)
+            self.dfh_ = t.dfh
+            self._Ppq, self._m1Ppq, self._wPpq, self._unfitted = t.Ppq, t.m1Ppq, t.wPpq, t.unfitted
+            self.mints_ = t.mints
         d = self.dfh_
         d.set_do_wK(self.do_wK_)
         self.engine = _lib.Engine(**self._engine_args)
@@ -216,25 +233,30 @@ class MemDFJK(JK):
             seed, amp = self._synthetic
             self.engine.fill_synthetic(_lib.TENSOR_PPQ, seed, amp)
         elif self._unfitted is not None:
-            # on-device fitting: the p-blocked loop of prepare_AO_core (dfhelper.cc:566-585) with the metric
-            # contraction + mirror copy (contract_metric_AO_core_symm, :1653-1678) done by the engine
-            sym, metric, block = self._unfitted
-            self.engine.set_metric(metric)
-            for m0 in range(0, d.nbf_, block):
-                m1 = min(d.nbf_, m0 + block)
-                self.engine.fit_rows(_lib.TENSOR_PPQ, m0, m1,
-                                     sym[int(d.symm_big_skips_[m0]):int(d.symm_big_skips_[m1])])
+            # on-device fitting: the p-blocked loop of prepare_AO_core / prepare_AO_wK_core (dfhelper.cc:566-585,
+            # :660-692) with the metric contraction + mirror copy (contract_metric_AO_core_symm, :1653-1678) done by
+            # the engine; wPpq_ takes no metric (:688-692), m1Ppq_ the full inverse (:642-650)
+            if self.do_wK_ and not all(w in self._unfitted for w in (_lib.TENSOR_M1PPQ, _lib.TENSOR_WPPQ)):
+                raise PsiException("MemDFJK: do_wK requires the m1Ppq and wPpq tensors")
+            for which in sorted(self._unfitted):
+                if which != _lib.TENSOR_PPQ and not self.do_wK_:
+                    continue
+                sym, metric = self._unfitted[which]
+                self.engine.set_metric(metric)
+                for m0 in range(0, d.nbf_, self._fit_block):
+                    m1 = min(d.nbf_, m0 + self._fit_block)
+                    self.engine.fit_rows(which, m0, m1, sym[int(d.symm_big_skips_[m0]):int(d.symm_big_skips_[m1])])
             self._unfitted = None
         else:
             if self._Ppq is None:
                 raise PsiException("MemDFJK: no Ppq tensor supplied")
             self.engine.upload(_lib.TENSOR_PPQ, self._Ppq)
-        if self.do_wK_:
-            # dfhelper.cc:199-206: wK needs the two extra in-core tensors
-            if self._m1Ppq is None or self._wPpq is None:
-                raise PsiException("MemDFJK: do_wK requires the m1Ppq and wPpq tensors")
-            self.engine.upload(_lib.TENSOR_M1PPQ, self._m1Ppq)
-            self.engine.upload(_lib.TENSOR_WPPQ, self._wPpq)
+            if self.do_wK_:
+                # dfhelper.cc:199-206: wK needs the two extra in-core tensors
+                if self._m1Ppq is None or self._wPpq is None:
+                    raise PsiException("MemDFJK: do_wK requires the m1Ppq and wPpq tensors")
+                self.engine.upload(_lib.TENSOR_M1PPQ, self._m1Ppq)
+                self.engine.upload(_lib.TENSOR_WPPQ, self._wPpq)
         # the host copies may be released now (the engine does not retain host pointers)
         self._Ppq = self._m1Ppq = self._wPpq = None
 

@@ -43,8 +43,6 @@ class DFTensors:
                  do_wK: bool = False, fit_on_device: bool = False, omega: float = 0.0):
         if do_wK and not omega > 0.0:
             raise ValueError("do_wK needs omega > 0 (JK::set_omega)")
-        if do_wK and fit_on_device:
-            raise NotImplementedError("wK tensors are fitted on the host in this driver")
         mints = MintsHelper(mol, primary)
         self.mints = mints
         self.dfh = DFHelper(primary.nbf(), aux.nbf())
@@ -55,20 +53,31 @@ class DFTensors:
         metric = mints.metric(aux)                                                 # prepare_metric :1462-1476
         self.Jm12 = matrix_power(metric, -0.5, condition)                          # compute_metric :1491-1517
         Amn = mints.three_center(aux)                                              # :1284-1347
-        self.Ppq = self.dense = self.unfitted_sym = self.m1Ppq = self.wPpq = None
+        self.Ppq = self.dense = self.m1Ppq = self.wPpq = None
+        self.unfitted = None  # tensor id -> (symmetric-packed unfitted integrals, metric power or None)
+        Jm1 = Wmn = None
         if do_wK:
             # prepare_AO_wK_core :589-699 -- m1Ppq_ = J^-1 (A|mn) (wmpower_ = -1.0), wPpq_ = (A|erf(omega r)/r|mn) unfitted
             self.dfh.set_do_wK(True)
-            self.m1Ppq = self.dfh.pack(np.tensordot(matrix_power(metric, -1.0, condition), Amn, axes=([1], [0])))
-            self.wPpq = self.dfh.pack(mints.three_center(aux, omega))
+            Jm1 = matrix_power(metric, -1.0, condition)
+            Wmn = mints.three_center(aux, omega)
         if fit_on_device:
-            # hand the unfitted n >= m half to the engine (b200jk_fit_rows); metric contraction + mirror run on the GPU
-            self.unfitted_sym = self.dfh.pack_symm(Amn)
+            # hand the unfitted n >= m half to the engine (b200jk_fit_rows); metric contraction + mirror run on the GPU.
+            # With wK: the same (A|mn) contracted with J^-1 for m1Ppq_ (:642-650, :678) and the erf-attenuated
+            # integrals scattered + mirrored with no metric for wPpq_ (:688-692).
+            sym = self.dfh.pack_symm(Amn)
+            self.unfitted = {0: (sym, self.Jm12)}
+            if do_wK:
+                self.unfitted[1] = (sym, Jm1)
+                self.unfitted[2] = (self.dfh.pack_symm(Wmn), None)
         else:
             # contract_metric_AO_core_symm :1653-1678  (B = J^-1/2 (A|mn)) on the host, then pack to pQq
             B = np.tensordot(self.Jm12, Amn, axes=([1], [0]))
             self.dense = B
             self.Ppq = self.dfh.pack(B)
+            if do_wK:
+                self.m1Ppq = self.dfh.pack(np.tensordot(Jm1, Amn, axes=([1], [0])))
+                self.wPpq = self.dfh.pack(Wmn)
 
 
 def build_jk(mol: Molecule, primary: BasisSet, aux: BasisSet, *, cutoff: float = 1e-12, condition: float = 1e-10,
@@ -76,20 +85,36 @@ def build_jk(mol: Molecule, primary: BasisSet, aux: BasisSet, *, cutoff: float =
              omega: float = 0.0):
     """JK::build_JK analogue.  jk_factory(dfh, Ppq) may construct another JK implementation (tests).
     fit_on_device: the engine contracts the metric itself (b200jk_set_metric / b200jk_fit_rows), fed in blocks of
-    fit_block basis functions like the p-blocked loop of prepare_AO_core."""
-    t = DFTensors(mol, primary, aux, cutoff, condition, fit_on_device=fit_on_device, do_wK=do_wK, omega=omega)
-    if fit_on_device:
-        jk = MemDFJK(t.dfh, ngpu=ngpu, unfitted=(t.unfitted_sym, t.Jm12, fit_block))
-    elif do_wK:
-        jk = (jk_factory or (lambda dfh, Ppq, m1, w: MemDFJK(dfh, Ppq, m1, w, ngpu=ngpu)))(t.dfh, t.Ppq, t.m1Ppq, t.wPpq)
+    fit_block basis functions like the p-blocked loop of prepare_AO_core.
+
+    As in the reference, the object is only CONFIGURED here: the integrals, the metric power and the packed tensors
+    are produced by jk.initialize() (MemDFJK::preiterations pushes cutoff / condition / omega / do_wK into DFHelper and
+    only then calls dfh_->initialize(), MemDFJK.cc:71-96), so set_cutoff / set_condition / set_omega / set_do_wK
+    between build and initialize take effect -- the order psi4's own initialize_jk uses (scf_iterator.py:112-135).
+    A jk_factory (an oracle-backed JK in the tests) takes ready-made host tensors and is therefore built eagerly."""
+    if jk_factory is not None:
+        t = DFTensors(mol, primary, aux, cutoff, condition, fit_on_device=False, do_wK=do_wK, omega=omega)
+        jk = jk_factory(t.dfh, t.Ppq, t.m1Ppq, t.wPpq) if do_wK else jk_factory(t.dfh, t.Ppq)
+        jk.mints_ = t.mints
+    else:
+        def provider(cutoff, condition, omega, do_wK):
+            return DFTensors(mol, primary, aux, cutoff, condition, do_wK=do_wK, fit_on_device=fit_on_device, omega=omega)
+
+        # the tables of the build-time cutoff size nbf / memory_estimate(); initialize() rebuilds them from the knobs
+        dfh = DFHelper(primary.nbf(), aux.nbf())
+        dfh.set_schwarz_cutoff(cutoff)
+        mints = MintsHelper(mol, primary)
+        dfh.prepare_blocking([primary.shell_nfunction(s) for s in range(primary.nshell())],
+                             [aux.shell_nfunction(s) for s in range(aux.nshell())])
+        dfh.prepare_sparsity(fun_max_vals=mints.schwarz_function_maxima())
+        jk = MemDFJK(dfh, ngpu=ngpu, provider=provider, fit_block=fit_block)
+        jk.mints_ = mints
+    if do_wK:
         jk.set_do_wK(True)
         jk.set_omega(omega)
-    else:
-        jk = (jk_factory or (lambda dfh, Ppq: MemDFJK(dfh, Ppq, ngpu=ngpu)))(t.dfh, t.Ppq)
     jk.set_cutoff(cutoff)
     if hasattr(jk, "set_condition"):
         jk.set_condition(condition)
-    jk.mints_ = t.mints
     jk.primary_ = primary
     return jk
 

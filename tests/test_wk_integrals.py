@@ -108,3 +108,48 @@ def test_gpu_wk_from_real_integrals(oracle):
     for got, want in ((jk.J()[0], jo.J()[0]), (jk.K()[0], jo.K()[0]), (jk.wK()[0], jo.wK()[0])):
         assert np.abs(got - want).max() < 1e-10
     jk.finalize()
+
+
+@pytest.mark.gpu
+def test_gpu_wk_with_on_device_fitting(oracle):
+    """prepare_AO_wK_core (dfhelper.cc:589-699) driven through the engine's fitting entry points: Ppq_ with J^-1/2,
+    m1Ppq_ with J^-1 (b200jk_set_metric + b200jk_fit_rows) and wPpq_ with no metric (b200jk_set_metric(NULL))."""
+    mol = water()
+    P, A = BasisSet.build(mol, "cc-pvdz"), BasisSet.build(mol, "cc-pvdz-jkfit")
+    jk = scf.build_jk(mol, P, A, do_wK=True, omega=0.4, fit_on_device=True, fit_block=7)
+    jk.initialize()
+    C = np.linalg.qr(np.random.default_rng(3).standard_normal((P.nbf(), 5)))[0]
+    jk.C_left_add(C)
+    jk.compute()
+    assert np.abs(jk.wK()[0] - dense_wk(mol, P, A, C, 0.4)).max() < 1e-10
+    _, _, _, jo, _ = run_wk(oracle_wk_factory(), 0.4)
+    for got, want in ((jk.J()[0], jo.J()[0]), (jk.K()[0], jo.K()[0]), (jk.wK()[0], jo.wK()[0])):
+        assert np.abs(got - want).max() < 1e-10
+    jk.finalize()
+
+
+@pytest.mark.gpu
+def test_gpu_knobs_set_between_build_and_initialize_take_effect(oracle):
+    """The reference configures after build and before initialize (scf_iterator.py:112-135: build_JK, set_do_wK /
+    set_omega / ..., initialize; MemDFJK::preiterations pushes the knobs into DFHelper first, MemDFJK.cc:71-96).
+    build_JK(do_wK=True) without an omega must not fail, and the omega set afterwards is the one wK uses."""
+    from psi4_b200 import JK
+
+    mol = water()
+    P, A = BasisSet.build(mol, "cc-pvdz"), BasisSet.build(mol, "cc-pvdz-jkfit")
+    jk = JK.build_JK(P, A, do_wK=True)  # no omega yet
+    jk.set_omega(0.4)
+    jk.set_condition(1e-10)
+    jk.initialize()
+    C = np.linalg.qr(np.random.default_rng(3).standard_normal((P.nbf(), 5)))[0]
+    jk.C_left_add(C)
+    jk.compute()
+    assert np.abs(jk.wK()[0] - dense_wk(mol, P, A, C, 0.4)).max() < 1e-10
+    assert "Omega:                4.000E-01" in jk.print_header()
+    jk.finalize()
+    # wK tasked, omega never set: initialize() refuses (the reference would build erf integrals with omega = 0)
+    from psi4_b200 import PsiException
+
+    jk2 = JK.build_JK(P, A, do_wK=True)
+    with pytest.raises(PsiException):
+        jk2.initialize()
