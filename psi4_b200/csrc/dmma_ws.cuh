@@ -246,6 +246,78 @@ __device__ __forceinline__ void consume_item_any(const WsCarve& sm, int bsb, int
 }
 
 // ---------------------------------------------------------------------------------------------
+// Diagonal tile of a symmetric product (K4 with T2 == T1), upper triangle only.  In units of 8 x 8 blocks the tile is
+// 16 x 16 and block (b, cb) is needed iff cb >= b: 136 of 256 blocks.  With the usual row-block deal (block b -> warp
+// b % 4) the four SM sub-partitions would get 40 / 36 / 32 / 28 blocks; dealing the odd groups in reverse -- row
+// blocks {wm, 7 - wm, 8 + wm, 15 - wm} -- gives every sub-partition exactly 34 (9 in its left-half warp, 25 in its
+// right-half warp).  Everything about the shape is a compile-time function of (WM, WN), so the DMMA stream stays
+// unpredicated; same software pipeline as consume_item.
+// ---------------------------------------------------------------------------------------------
+template <int WM, int WN>
+struct DiagShape {
+    static __host__ __device__ constexpr int rowsel(int mb) { return (mb & 1) ? 3 - WM : WM; }
+    static __host__ __device__ constexpr int nb0(int mb) {
+        const int b = mb * 4 + rowsel(mb) - 8 * WN;
+        return b < 0 ? 0 : (b > 8 ? 8 : b);
+    }
+    static __host__ __device__ constexpr bool row_live(int mb) { return nb0(mb) < 8; }
+    static __host__ __device__ constexpr int a_off(int mb) { return mb * WS_A_MB_STRIDE + (rowsel(mb) - WM) * 8 * WS_ROW_BYTES; }
+    static __host__ __device__ constexpr int nb_first() {
+        int f = 8;
+        for (int mb = 0; mb < 4; mb++) f = nb0(mb) < f ? nb0(mb) : f;
+        return f;
+    }
+};
+__device__ __forceinline__ int diag_row_of(int mb, int wm) { return mb * 4 + ((mb & 1) ? 3 - wm : wm); }  // 8-row block
+
+template <int WM, int WN>
+__device__ __forceinline__ void consume_item_diag(const WsCarve& sm, int b_stage_bytes, int a_row0, int b_row0,
+                                                  const int (&off)[4], double (&acc)[4][8][2], int nkt, uint32_t& g, int lane) {
+    using S = DiagShape<WM, WN>;
+    constexpr int NB = 8;
+    constexpr int NF = S::nb_first();
+    double a[2][4], b[2][NB];
+    int s = g % WS_STAGES;
+    const uint8_t* ap = sm.As + s * WS_A_STAGE + a_row0;
+    const uint8_t* bp = sm.Bs + s * b_stage_bytes + b_row0;
+    auto load = [&](int buf, int o) {
+#pragma unroll
+        for (int mb = 0; mb < 4; mb++)
+            if (S::row_live(mb)) a[buf][mb] = *reinterpret_cast<const double*>(ap + S::a_off(mb) + o);
+#pragma unroll
+        for (int nb = NF; nb < NB; nb++) b[buf][nb] = *reinterpret_cast<const double*>(bp + nb * 8 * WS_ROW_BYTES + o);
+    };
+    load(0, off[0]);
+    for (int kt = 0; kt < nkt; kt++, g++) {
+        const bool has_next = kt + 1 < nkt;
+        const int sn = (g + 1) % WS_STAGES;
+        const uint32_t pn = ((g + 1) / WS_STAGES) & 1;
+        const uint32_t ready = has_next ? mbar_test(&sm.full[sn], pn) : 0;
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++) {
+            const int cur = ks & 1, nxt = cur ^ 1;
+            if (ks < 3) {
+                load(nxt, off[ks + 1]);
+            } else {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.empty[g % WS_STAGES]);
+                if (has_next) {
+                    if (!ready) mbar_wait(&sm.full[sn], pn);
+                    ap = sm.As + sn * WS_A_STAGE + a_row0;
+                    bp = sm.Bs + sn * b_stage_bytes + b_row0;
+                    load(nxt, off[0]);
+                }
+            }
+#pragma unroll
+            for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+                for (int nb = 0; nb < NB; nb++)
+                    if (nb >= S::nb0(mb)) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[cur][mb], b[cur][nb]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K3, persistent.  Work item w -> (it, qt, m): it fastest so the CTAs sharing an A tile run together.
 // ---------------------------------------------------------------------------------------------
 struct HalfWsParams {
@@ -492,6 +564,7 @@ struct KgemmWsParams {
     // mirrored for T2 == T1.  nullptr: partials only, kgemm_reduce_list_kernel follows (B200JK_KREDUCE=separate).
     int* arrive;        // [ntiles * 8], zeroed before launch
     int nsplit;
+    int tri;            // triangular consumer on whole diagonal tiles (B200JK_KTRI=0 turns it off for A/B runs)
     double* K;          // [nbf][nbf]
 };
 
@@ -566,17 +639,33 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         // of the upper-right one and is not computed -- the warps of the left column half stop after their first two
         // row groups.  (The diagonal quadrants are still computed whole; only their upper triangles are kept.)
         const bool diag = p.symmetric && tl.x == tl.y;
-        if (diag && wn == 0) mbv = min(mbv, 2);
+        // a diagonal tile that lies wholly inside the matrix takes the triangular consumer (34 of 64 block products per
+        // sub-partition instead of 48); the ragged last one keeps the quadrant rule
+        const bool tri = diag && p.tri && (tl.x + 1) * BM <= p.nbf;
+        if (diag && !tri && wn == 0) mbv = min(mbv, 2);
         double acc[4][NB][2];
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
             for (int b = 0; b < NB; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
-        consume_item_any<NB>(sm, B_STAGE, a_row0, b_row0, off, acc, nkt, g, lane, mbv, nbv);
+        if (tri) {
+            switch (cw) {
+                case 0: consume_item_diag<0, 0>(sm, B_STAGE, a_row0, b_row0, off, acc, nkt, g, lane); break;
+                case 1: consume_item_diag<1, 0>(sm, B_STAGE, a_row0, b_row0, off, acc, nkt, g, lane); break;
+                case 2: consume_item_diag<2, 0>(sm, B_STAGE, a_row0, b_row0, off, acc, nkt, g, lane); break;
+                case 3: consume_item_diag<3, 0>(sm, B_STAGE, a_row0, b_row0, off, acc, nkt, g, lane); break;
+                case 4: consume_item_diag<0, 1>(sm, B_STAGE, a_row0, b_row0, off, acc, nkt, g, lane); break;
+                case 5: consume_item_diag<1, 1>(sm, B_STAGE, a_row0, b_row0, off, acc, nkt, g, lane); break;
+                case 6: consume_item_diag<2, 1>(sm, B_STAGE, a_row0, b_row0, off, acc, nkt, g, lane); break;
+                default: consume_item_diag<3, 1>(sm, B_STAGE, a_row0, b_row0, off, acc, nkt, g, lane); break;
+            }
+        } else {
+            consume_item_any<NB>(sm, B_STAGE, a_row0, b_row0, off, acc, nkt, g, lane, mbv, nbv);
+        }
         double* wsp = p.ws + (size_t)w * (BM * BN);
 #pragma unroll
         for (int mb = 0; mb < 4; mb++) {
-            int r = mb * 32 + wm * 8 + gq;
+            int r = (tri ? diag_row_of(mb, wm) : mb * 4 + wm) * 8 + gq;
 #pragma unroll
             for (int nb = 0; nb < NB; nb++) {
                 int c = wn * 8 * NB + nb * 8 + t * 2;
@@ -600,7 +689,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
                 const size_t sstride = (size_t)p.ntiles * (BM * BN);
 #pragma unroll 1
                 for (int mb = 0; mb < mbv; mb++) {
-                    const int r = mb * 32 + wm * 8 + gq;
+                    const int r = (tri ? diag_row_of(mb, wm) : mb * 4 + wm) * 8 + gq;
                     const double* base = src0 + r * BN;
                     double2 sum[NB];
 #pragma unroll

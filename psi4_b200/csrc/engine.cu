@@ -539,6 +539,12 @@ int run_kgemm_ws(b200jk* h, Shard& s, const double* T1, const double* T2, int kd
         const char* e = getenv("B200JK_KREDUCE");
         separate = (e && !strcmp(e, "separate")) ? 1 : 0;
     }
+    static int tri = -1;
+    if (tri < 0) {
+        const char* e = getenv("B200JK_KTRI");
+        tri = (e && e[0] == '0') ? 0 : 1;
+    }
+    p.tri = (tri && !separate) ? 1 : 0;  // (the separate reduce kernel reads partial tiles in the plain row order: same)
     p.arrive = separate ? nullptr : s.d_counter + 1;
     p.nsplit = nsplit;
     p.K = Kout;
