@@ -148,6 +148,29 @@ int b200jk_compute_device(b200jk_t* h, int nmat, const double* const* dCl, const
                           const int* nocc, const double* const* dD, double* const* dJ, double* const* dK,
                           double* const* dwK, int do_J, int do_K, int do_wK);
 
+/* ---- density-fitted SCF gradient: the tensor contractions of DFJKGrad -------------------
+ * Replaces the CPU work of scfgrad/jk_grad.cc build_Amn_terms (:294-475), build_AB_inv_terms (:634-721), build_UV_terms
+ * (:722-833) and the AO back-transform at the top of build_Amn_x_terms (:1010-1023) -- everything of
+ * DFJKGrad::compute_gradient except the Libint2 derivative integrals (A|B)^x, (A|mn)^x and their final dot products,
+ * which stay in psi4.  Nothing is recomputed: the intermediates come from the fitted tensor that is already resident
+ * (one first-J-sweep pass and one half transform per spin) and the metric power the caller passes.
+ *
+ * b200jk_grad_begin   nspin = 1: restricted (the reference's Ca_ == Cb_: one transform, factor 2), 2: unrestricted.
+ *                     C[s]: nbf x nocc[s] occupied orbitals (Ca_occ, Cb_occ); Dt: nbf x nbf total density (Da + Db,
+ *                     symmetric); Jm12: naux x naux, the same J^-1/2 the tensor was fitted with.
+ * b200jk_grad_vectors d[naux]        = J^-1 (A|mn) Dt_mn                       (the "c" entry after :659)
+ *                     V[naux x naux] = f sum_spin sum_ij (A|ij)(B|ij), fitted   (the "V" entry, :812)
+ * b200jk_grad_rows    Kmn[(a1-a0) x nbf x nbf] = f sum_spin C (A|ij) C^T for aux rows [a0, a1): what the reference
+ *                     holds in Kmnp for one block of auxiliary shells (:1010-1023); call it block by block and dot
+ *                     each block with (A|mn)^x on the host.
+ * b200jk_grad_end     frees the intermediates.
+ * One-shard handles only (the gradient runs once per geometry). */
+int b200jk_grad_begin(b200jk_t* h, int nspin, const double* const* C, const int* nocc, const double* Dt,
+                      const double* Jm12);
+int b200jk_grad_vectors(b200jk_t* h, double* d, double* V);
+int b200jk_grad_rows(b200jk_t* h, size_t a0, size_t a1, double* Kmn);
+int b200jk_grad_end(b200jk_t* h);
+
 /* ---- introspection ---------------------------------------------------------------------------- */
 
 typedef struct {

@@ -25,6 +25,7 @@
 #include "dmma_ws.cuh"
 #include "fit_kernels.cuh"
 #include "j_kernels.cuh"
+#include "gemm_strided.cuh"
 #include "peer_reduce.cuh"
 
 using namespace b2k;
@@ -197,9 +198,22 @@ struct b200jk {
         double flops;
     };
     std::vector<FitTiming> fit_pending;  // metric-GEMM event pairs not yet read back
+    // DF-JK gradient intermediates (grad_host.inl), alive between b200jk_grad_begin and b200jk_grad_end
+    struct Grad {
+        struct Spin {
+            double* C = nullptr;     // [nbf][o] occupied orbitals
+            double* cfit = nullptr;  // [naux][o][op] fitted (A|ij)
+            int o = 0, op = 0;
+        } spin[2];
+        double *Jm12 = nullptr, *d = nullptr, *V = nullptr, *rows = nullptr, *M1 = nullptr;
+        size_t rows_cap = 0, M1_cap = 0;
+        int nspin = 0;
+        bool active = false;
+    } grad;
 };
 
 namespace {
+void grad_free(b200jk* h);  // grad_host.inl
 // true if [p, p+bytes) lies inside a range the caller registered (page-locked): DMA can use it directly
 bool is_pinned(const b200jk* h, const void* p, size_t bytes) {
     const char* c = (const char*)p;
@@ -1249,6 +1263,7 @@ void b200jk_destroy(b200jk_t* h) {
         cudaEventDestroy(f.a);
         cudaEventDestroy(f.b);
     }
+    grad_free(h);
     for (auto& s : h->sh) peer_free(h, s);
     for (auto& s : h->sh) free_shard(s);
     for (auto& sl : h->stage) {
@@ -1937,3 +1952,4 @@ int b200jk_fp64_peak(b200jk_t* h, int kind, double seconds, double* out4) {
 }  // extern "C"
 
 #include "fit_host.inl"
+#include "grad_host.inl"

@@ -72,6 +72,10 @@ SIGNATURES = {
     "b200jk_set_metric": (ct.c_int, [ct.c_void_p, _dp]),
     "b200jk_fit_rows": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_size_t, ct.c_size_t, _dp]),
     "b200jk_fit_stats": (ct.c_int, [ct.c_void_p, _dp, _dp]),
+    "b200jk_grad_begin": (ct.c_int, [ct.c_void_p, ct.c_int, _dpp, ct.POINTER(ct.c_int), _dp, _dp]),
+    "b200jk_grad_vectors": (ct.c_int, [ct.c_void_p, _dp, _dp]),
+    "b200jk_grad_rows": (ct.c_int, [ct.c_void_p, ct.c_size_t, ct.c_size_t, _dp]),
+    "b200jk_grad_end": (ct.c_int, [ct.c_void_p]),
 }
 
 
@@ -276,6 +280,30 @@ class Engine:
         no = (ct.c_int * nmat)(*nocc)
         self._check(self.L.b200jk_compute_device(self.h, nmat, arr(dCl), arr(dCr), no, arr(dD), arr(dJ), arr(dK),
                                                  arr(dwK), int(do_J), int(do_K), int(do_wK)))
+
+    # -- DF-JK gradient intermediates (scfgrad/jk_grad.cc) --
+    def grad_begin(self, C, Dt, Jm12):
+        """C: [Ca_occ] (restricted) or [Ca_occ, Cb_occ]; Dt: total density; Jm12: the J^-1/2 the tensor was fitted with."""
+        n = self.nbf
+        Cs = [np.ascontiguousarray(c, dtype=np.float64).reshape(n, -1) for c in C]
+        nocc = (ct.c_int * len(Cs))(*[c.shape[1] for c in Cs])
+        Dt = np.ascontiguousarray(Dt, dtype=np.float64)
+        J = np.ascontiguousarray(Jm12, dtype=np.float64)
+        assert Dt.shape == (n, n) and J.shape == (self.naux, self.naux)
+        self._check(self.L.b200jk_grad_begin(self.h, len(Cs), _ptr_array(Cs), nocc, _d(Dt), _d(J)))
+
+    def grad_vectors(self):
+        d, V = np.empty(self.naux), np.empty((self.naux, self.naux))
+        self._check(self.L.b200jk_grad_vectors(self.h, _d(d), _d(V)))
+        return d, V
+
+    def grad_rows(self, a0, a1):
+        out = np.empty((a1 - a0, self.nbf, self.nbf))
+        self._check(self.L.b200jk_grad_rows(self.h, a0, a1, _d(out)))
+        return out
+
+    def grad_end(self):
+        self._check(self.L.b200jk_grad_end(self.h))
 
     def stats(self) -> dict:
         s = Stats()

@@ -16,7 +16,8 @@ WANT = {
     "aug-cc-pvdz": ["H", "C", "O"],
     "aug-cc-pvdz-jkfit": ["H", "C", "O"],
     "def2-svp": ["H", "C"],
-    "def2-universal-jkfit": ["H", "C"],
+    "def2-universal-jkfit": ["H", "C", "O"],
+    "sto-3g": ["H", "O"],
 }
 
 

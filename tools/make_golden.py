@@ -85,6 +85,20 @@ anchors = {
         "geometry_angstrom_output_ref": geometry_block("dfscf-bz2/output.ref"),
         "nbf": 228, "naux": 1116,
     },
+    "fd_gradient_h2o_sto3g": {
+        "source": "tests/fd-gradient/input.dat:3-14 (gradient('scf'), default scf_type DF) ; output.ref:109-114 (geometry), "
+                  ":184-189 (auxiliary basis = def2-universal-jkfit data), :241 (energy), :330-335 (analytic total gradient)",
+        "basis": "sto-3g", "aux": "def2-universal-jkfit", "naux": 113,
+        "geometry_angstrom_output_ref": geometry_block("fd-gradient/output.ref"),
+        "nuclear_repulsion_output_ref": grab("fd-gradient/output.ref", r"Nuclear repulsion =\s+(\d+\.\d+)"),
+        "scf_total_energy_output_ref": grab("fd-gradient/output.ref", r"Total Energy =\s+(-\d+\.\d+)"),
+        "total_gradient_output_ref": [[float(x) for x in row] for row in re.findall(
+            r"^\s+[123]\s+(-?\d+\.\d+)\s+(-?\d+\.\d+)\s+(-?\d+\.\d+)\s*$",
+            open(os.path.join(REF, "fd-gradient/output.ref")).read().split("-Total Gradient:")[1].split("tstop")[0], re.M)],
+        "tolerance_decimals": 6,
+        "note": "the only in-tree DF-SCF gradient whose numbers are committed without an XC functional or an external "
+                "potential; the input compares it with finite differences of the energy to 1e-8 (input.dat:30)",
+    },
     "jkmemory_ar5": {
         "source": "tests/pytests/test_jkmemory.py:12-18,44,49 (MEM_DF rows, one thread, memory=1e9, do_wK=False)",
         "geometry_angstrom": [["Ar", 0.0, 0.0, z] for z in (0.0, 5.0, 15.0, 25.0, 35.0)],
