@@ -568,6 +568,87 @@ struct KgemmWsParams {
     double* K;          // [nbf][nbf]
 };
 
+// Count consumer warp cw's part of item w's partial tile as stored; true if that makes the tile's part complete
+// (every split has arrived), i.e. this warp must now sum it.
+__device__ __forceinline__ bool kgemm_arrive(const KgemmWsParams& p, int w, int cw, int lane) {
+    __threadfence();  // this lane's part of the partial tile is visible device-wide ...
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) last = (atomicAdd(p.arrive + (w % p.ntiles) * WS_CONSUMER_WARPS + cw, 1) == p.nsplit - 1) ? 1 : 0;
+    return __shfl_sync(0xffffffffu, last, 0) != 0;  // ... before the warp is counted
+}
+
+// Consumer warp cw's 32 x 64 part of the tile of item w, summed over the splits in split order (fixed order: the
+// result does not depend on who arrives last), accumulated into K (beta = 1 across Q chunks) and mirrored when
+// T2 == T1.  One 8-row group at a time with eight splits' worth of loads (64 x 16 bytes per lane) in flight: this
+// runs when the warp's accumulators are dead.  Dead edge columns of a partial tile hold zeros, so only the stores
+// are predicated.
+__device__ __noinline__ void kgemm_reduce_part(const KgemmWsParams& p, int w, int cw, int lane) {
+    constexpr int NB = 8, BN = 128;
+    const int wm = cw & 3, wn = cw >> 2, gq = lane >> 2, t = lane & 3;
+    const int tile = w % p.ntiles;
+    const int2 tl = p.tiles[tile];
+    int mbv = live_row_blocks(p.nbf - tl.x * BM, wm);
+    const int nbv = max(0, min(NB, (p.nbf - (tl.y * BN + wn * 8 * NB) + 7) / 8));
+    const bool diag = p.symmetric && tl.x == tl.y;
+    const bool tri = diag && p.tri && (tl.x + 1) * BM <= p.nbf;
+    if (diag && !tri && wn == 0) mbv = min(mbv, 2);
+    __threadfence();
+    const double* src0 = p.ws + (size_t)tile * (BM * BN) + wn * 8 * NB + t * 2;
+    const size_t sstride = (size_t)p.ntiles * (BM * BN);
+    constexpr int U = 8;
+#pragma unroll 1
+    for (int mb = 0; mb < mbv; mb++) {
+        const int r = (tri ? diag_row_of(mb, wm) : mb * 4 + wm) * 8 + gq;
+        const double* base = src0 + r * BN;
+        double2 sum[NB];
+#pragma unroll
+        for (int nb = 0; nb < NB; nb++) sum[nb] = make_double2(0.0, 0.0);
+        int sp = 0;
+#pragma unroll 1
+        for (; sp + U <= p.nsplit; sp += U) {
+            double2 v[U][NB];
+#pragma unroll
+            for (int u = 0; u < U; u++)
+#pragma unroll
+                for (int nb = 0; nb < NB; nb++)
+                    v[u][nb] = __ldcg(reinterpret_cast<const double2*>(base + (size_t)(sp + u) * sstride + nb * 8));
+#pragma unroll
+            for (int u = 0; u < U; u++)
+#pragma unroll
+                for (int nb = 0; nb < NB; nb++) {
+                    sum[nb].x += v[u][nb].x;
+                    sum[nb].y += v[u][nb].y;
+                }
+        }
+#pragma unroll 1
+        for (; sp < p.nsplit; sp++) {
+#pragma unroll
+            for (int nb = 0; nb < NB; nb++) {
+                const double2 v = __ldcg(reinterpret_cast<const double2*>(base + (size_t)sp * sstride + nb * 8));
+                sum[nb].x += v.x;
+                sum[nb].y += v.y;
+            }
+        }
+        const int m = tl.x * BM + r;
+        if (m < p.nbf) {
+#pragma unroll
+            for (int nb = 0; nb < NB; nb++) {
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int c = wn * 8 * NB + nb * 8 + t * 2 + e;
+                    const int n = tl.y * BN + c;
+                    if (nb < nbv && n < p.nbf && (!diag || c >= r)) {
+                        const double v = e ? sum[nb].y : sum[nb].x;
+                        p.K[(size_t)m * p.nbf + n] += v;
+                        if (p.symmetric && n != m) p.K[(size_t)n * p.nbf + m] += v;
+                    }
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(WS_THREADS, 1)
     kgemm_ws_kernel(const __grid_constant__ CUtensorMap t1map, const __grid_constant__ CUtensorMap t2map, KgemmWsParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -624,6 +705,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
     const int a_row0 = (wm * 8 + gq) * WS_ROW_BYTES;  // row blocks interleaved over the four M warps
     const int b_row0 = (wn * 8 * NB + gq) * WS_ROW_BYTES;
     uint32_t g = 0;
+    int pending = -1;  // the item whose partial tile this warp has stored but not yet counted
     for (;;) {
         int s = g % WS_STAGES;
         mbar_wait(&sm.full[s], (g / WS_STAGES) & 1);
@@ -662,6 +744,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         } else {
             consume_item_any<NB>(sm, B_STAGE, a_row0, b_row0, off, acc, nkt, g, lane, mbv, nbv);
         }
+        // The PREVIOUS item of this warp is counted now, one whole item after its partial tile was stored: the fence
+        // finds those stores long drained.  (Fencing right behind the stores held the DMMA pipe of this sub-partition
+        // idle for the drain time of 128 KB, once per item.)
+        const bool reduce_prev = p.arrive && pending >= 0 && kgemm_arrive(p, pending, cw, lane);
         double* wsp = p.ws + (size_t)w * (BM * BN);
 #pragma unroll
         for (int mb = 0; mb < 4; mb++) {
@@ -672,74 +758,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
                 *reinterpret_cast<double2*>(wsp + r * BN + c) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
             }
         }
-        if (p.arrive) {
-            const int tile = w % p.ntiles;
-            __threadfence();  // this lane's part of the partial tile is visible device-wide ...
-            __syncwarp();
-            int last = 0;
-            if (lane == 0) last = (atomicAdd(p.arrive + tile * WS_CONSUMER_WARPS + cw, 1) == p.nsplit - 1) ? 1 : 0;
-            last = __shfl_sync(0xffffffffu, last, 0);  // ... before the warp is counted
-            if (last) {
-                __threadfence();
-                // This warp's 32 x 64 part of the tile, summed over the splits in split order, one 8-row group at a
-                // time: the accumulators are dead by now, so four splits' worth of loads (32 x 16 bytes per lane) can be
-                // in flight at once -- with one split at a time this loop was latency-bound (~1.5 ms at the end of the
-                // kernel).  Dead edge columns of a partial tile hold zeros, so only the stores are predicated.
-                const double* src0 = p.ws + (size_t)tile * (BM * BN) + wn * 8 * NB + t * 2;
-                const size_t sstride = (size_t)p.ntiles * (BM * BN);
-#pragma unroll 1
-                for (int mb = 0; mb < mbv; mb++) {
-                    const int r = (tri ? diag_row_of(mb, wm) : mb * 4 + wm) * 8 + gq;
-                    const double* base = src0 + r * BN;
-                    double2 sum[NB];
-#pragma unroll
-                    for (int nb = 0; nb < NB; nb++) sum[nb] = make_double2(0.0, 0.0);
-                    int sp = 0;
-#pragma unroll 1
-                    for (; sp + 4 <= p.nsplit; sp += 4) {
-                        double2 v[4][NB];
-#pragma unroll
-                        for (int u = 0; u < 4; u++)
-#pragma unroll
-                            for (int nb = 0; nb < NB; nb++)
-                                v[u][nb] = __ldcg(reinterpret_cast<const double2*>(base + (size_t)(sp + u) * sstride + nb * 8));
-#pragma unroll
-                        for (int u = 0; u < 4; u++)
-#pragma unroll
-                            for (int nb = 0; nb < NB; nb++) {
-                                sum[nb].x += v[u][nb].x;
-                                sum[nb].y += v[u][nb].y;
-                            }
-                    }
-#pragma unroll 1
-                    for (; sp < p.nsplit; sp++) {
-#pragma unroll
-                        for (int nb = 0; nb < NB; nb++) {
-                            const double2 v = __ldcg(reinterpret_cast<const double2*>(base + (size_t)sp * sstride + nb * 8));
-                            sum[nb].x += v.x;
-                            sum[nb].y += v.y;
-                        }
-                    }
-                    const int m = tl.x * BM + r;
-                    if (m < p.nbf) {
-#pragma unroll
-                        for (int nb = 0; nb < NB; nb++) {
-#pragma unroll
-                            for (int e = 0; e < 2; e++) {
-                                const int c = wn * 8 * NB + nb * 8 + t * 2 + e;
-                                const int n = tl.y * BN + c;
-                                if (nb < nbv && n < p.nbf && (!diag || c >= r)) {
-                                    const double v = e ? sum[nb].y : sum[nb].x;
-                                    p.K[(size_t)m * p.nbf + n] += v;
-                                    if (p.symmetric && n != m) p.K[(size_t)n * p.nbf + m] += v;
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-        }
+        if (reduce_prev) kgemm_reduce_part(p, pending, cw, lane);
+        pending = w;
     }
+    // the last item of this CTA: nothing follows it, retire it now
+    if (p.arrive && pending >= 0 && kgemm_arrive(p, pending, cw, lane)) kgemm_reduce_part(p, pending, cw, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
