@@ -395,10 +395,15 @@ def measure(args, ds, name, steps, warmup, headline):
 
     # ---- determinism: the two arms, and the first and the last host-arm build, agree bit for bit ----
     arms_equal = run_equal = True
+    arms_diff = {}
     if fetch:
         for i in range(nmat):
-            arms_equal = arms_equal and np.array_equal(eng.dev_get(dJ[i], (nbf, nbf)), J[i]) \
-                and np.array_equal(eng.dev_get(dK[i], (nbf, nbf)), K[i])
+            for tag, dev, host in (("J", dJ[i], J[i]), ("K", dK[i], K[i])):
+                got = eng.dev_get(dev, (nbf, nbf))
+                if not np.array_equal(got, host):
+                    arms_equal = False
+                    arms_diff[f"{tag}[{i}]"] = {"max_abs": float(np.abs(got - host).max()),
+                                                "n_differ": int(np.count_nonzero(got != host))}
             if first is not None:
                 run_equal = run_equal and np.array_equal(first[0][i], J[i]) and np.array_equal(first[1][i], K[i])
     # every rank's device-arm result is the same bits (the sum is formed once per element and broadcast)
@@ -416,7 +421,7 @@ def measure(args, ds, name, steps, warmup, headline):
                    2: "NCCL all-reduce"}.get(st_dev["reduce_kind"], "?")
     eng.close()
     res = dict(cfg=cfg, keep=keep, amp=amp, Cl=Cl, Crl=Crl, value=value, wall_ms=wall_ms, parts=parts, st_dev=st_dev,
-               e2e_ms=e2e_ms, e2e_parts=e2e_parts, launches=launches, clk=clk, arms_equal=bool(arms_equal),
+               e2e_ms=e2e_ms, e2e_parts=e2e_parts, launches=launches, clk=clk, arms_equal=bool(arms_equal), arms_diff=arms_diff,
                run_equal=bool(run_equal), ranks_equal=bool(ranks_equal), spot=spot, pk_dmma=pk_dmma, pk_dfma=pk_dfma,
                layout_s=layout_s, fill_s=fill_s, reduce_kind=reduce_kind,
                h2d=int(nmat * (Cl[0].nbytes * (1 if Crl is None else 2) + n2b)), d2h=int(nmat * 2 * n2b))
@@ -579,7 +584,7 @@ def main():
     for nm, r in extra.items():
         kt, _ = kernel_table(r, peak_dmma, hbm_peak, peak_src)
         wl[nm] = {"config": config_of(nm, r["cfg"], r["keep"], r["Crl"]), "value_ms": r["value"], "e2e_ms": r["e2e_ms"],
-                  "kernels": kt, "parity_spot": r["spot"], "arms_bit_identical": r["arms_equal"],
+                  "kernels": kt, "parity_spot": r["spot"], "arms_bit_identical": r["arms_equal"], "arms_diff": r["arms_diff"],
                   "run_to_run_bit_identical": r["run_equal"], "ranks_bit_identical": r["ranks_equal"],
                   "gpu_launches": int(r["launches"]), "hbm_tensor_gb": r["st_dev"]["hbm_tensor_bytes"] / 1e9}
 
@@ -590,7 +595,7 @@ def main():
         "e2e": {"value": res["e2e_ms"], "unit": "ms", "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"],
                 "ms_h2d": res["e2e_parts"]["ms_h2d"], "ms_d2h": res["e2e_parts"]["ms_d2h"]},
         "gpu_launches": int(res["launches"]), "roofline": roofline, "cpu_baseline": cb, "kernels": kernels, "clocks": res["clk"],
-        "wall_ms_per_step": res["wall_ms"], "arms_bit_identical": res["arms_equal"],
+        "wall_ms_per_step": res["wall_ms"], "arms_bit_identical": res["arms_equal"], "arms_diff": res["arms_diff"],
         "run_to_run_bit_identical": res["run_equal"], "ranks_bit_identical": res["ranks_equal"],
         "parity_spot": res["spot"], "workloads": wl,
         "hbm": {"tensor_gb": res["st_dev"]["hbm_tensor_bytes"] / 1e9, "work_gb": res["st_dev"]["hbm_work_bytes"] / 1e9,

@@ -1756,7 +1756,9 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
             CK(cudaSetDevice(h->sh[si].dev));
             CK(cudaStreamWaitEvent(h->sh[si].copy, evK[si], 0));
         }
-        if ((rc = reduce_shards(h, ol.offK, ol.countKW, true, 0, 0))) return rc;
+        // (result into every shard's window: in rank mode any rank may ask for the outputs, and a rank cannot know
+        // whether its peers do; the extra NVLink writes are count doubles per rank, ~0.05 ms at C60)
+        if ((rc = reduce_shards(h, ol.offK, ol.countKW, true, 0, -1))) return rc;
         CK(cudaSetDevice(s0.dev));
         if (ol.countKW && fetch) {
             Phase ph;
@@ -1777,7 +1779,7 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
         }
         evKhome = get_event(s0);
         CK(cudaEventRecord(evKhome, s0.copy));
-        if ((rc = reduce_shards(h, ol.offJ, ol.countJ, false, 1, 0))) return rc;
+        if ((rc = reduce_shards(h, ol.offJ, ol.countJ, false, 1, -1))) return rc;
         CK(cudaSetDevice(s0.dev));
         if (ol.countJ && fetch) {
             PhaseScope ps(s0, 5);
