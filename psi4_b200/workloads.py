@@ -26,6 +26,8 @@ CONFIGS = {
     "h2o40_tz": dict(nbf=2320, naux=5560, nocc=200, nmat=2, mask="h2o40_cc-pvtz_1e-12"),
     # one eighth of C60's auxiliary index (what each GPU holds at 8 GPUs): short enough for ncu --set full
     "c60_tz_q8": dict(nbf=1800, naux=592, nocc=180, nmat=1, mask="c60_cc-pvtz_1e-12"),
+    # one eighth of (H2O)40's auxiliary index: the per-GPU shard of the 8-GPU UHF run (two densities, gather path)
+    "h2o40_tz_q8": dict(nbf=2320, naux=695, nocc=200, nmat=2, mask="h2o40_cc-pvtz_1e-12"),
     # SCREENING=NONE analogue (jk.cc:60-61): every pair kept, the dense upper bound of SURVEY.md section 8
     "c60_tz_dense": dict(nbf=1800, naux=4740, nocc=180, nmat=1, mask=None),
 }
