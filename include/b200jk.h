@@ -171,6 +171,17 @@ int b200jk_grad_vectors(b200jk_t* h, double* d, double* V);
 int b200jk_grad_rows(b200jk_t* h, size_t a0, size_t a1, double* Kmn);
 int b200jk_grad_end(b200jk_t* h);
 
+/* ---- setup: Matrix::power on the device --------------------------------------------------------------------------
+ * Matrix::power(alpha, cutoff) (libmints/matrix.cc:2370-2424) as DFHelper::prepare_metric / compute_metric call it for
+ * the fitting metric (lib3index/dfhelper.cc:1462-1517; alpha = -1/2 for Ppq_, -1 for m1Ppq_): eigendecomposition,
+ * eigenvalues with |lambda| < cutoff * max|lambda| dropped when alpha < 0 (and any non-finite lambda^alpha), then
+ * V f(Lambda) V^T.  A and out are n x n row-major host arrays (A symmetric; may alias).  remaining: eigenvalues kept (the
+ * Dimension the reference returns); ms_device: device time of the decomposition + reconstruction.  The decomposition is
+ * cuSOLVER's (dlopen'ed); the drop rule is evaluated on the host with the reference's own libm pow; the reconstruction
+ * runs in the engine's kernels. */
+int b200jk_matrix_power(b200jk_t* h, size_t n, const double* A, double alpha, double cutoff, double* out,
+                        int* remaining, double* ms_device);
+
 /* ---- introspection ---------------------------------------------------------------------------- */
 
 typedef struct {

@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <string>
 #include <chrono>
 #include <thread>
@@ -1955,3 +1956,4 @@ int b200jk_fp64_peak(b200jk_t* h, int kind, double seconds, double* out4) {
 
 #include "fit_host.inl"
 #include "grad_host.inl"
+#include "power_host.inl"

@@ -218,16 +218,18 @@ class MemDFJK(JK):
         """MemDFJK.cc:71-96: configure, then move the in-core tensors into HBM (Q-sharded)."""
         if self.engine is not None:
             return
+        self.engine = _lib.Engine(**self._engine_args)
         if self._provider is not None:
             if self.do_wK_ and not self.omega_ > 0.0:
                 raise PsiException("MemDFJK: wK tasked but omega is not set (JK::set_omega)")
-            t = self._provider(self.cutoff_, self.condition_, self.omega_, self.do_wK_)
+            # the metric powers (Matrix::power, the O(naux^3) step of the setup) run on the device too
+            t = self._provider(self.cutoff_, self.condition_, self.omega_, self.do_wK_, power=self.engine.matrix_power)
             self.dfh_ = t.dfh
             self._Ppq, self._m1Ppq, self._wPpq, self._unfitted = t.Ppq, t.m1Ppq, t.wPpq, t.unfitted
             self.mints_ = t.mints
+            self.Jm12_ = t.Jm12
         d = self.dfh_
         d.set_do_wK(self.do_wK_)
-        self.engine = _lib.Engine(**self._engine_args)
         self.engine.set_layout(d.nbf_, d.naux_, d.small_skips_, d.big_skips_, d.schwarz_fun_index_)
         if self._synthetic is not None:
             seed, amp = self._synthetic

@@ -76,6 +76,8 @@ SIGNATURES = {
     "b200jk_grad_vectors": (ct.c_int, [ct.c_void_p, _dp, _dp]),
     "b200jk_grad_rows": (ct.c_int, [ct.c_void_p, ct.c_size_t, ct.c_size_t, _dp]),
     "b200jk_grad_end": (ct.c_int, [ct.c_void_p]),
+    "b200jk_matrix_power": (ct.c_int, [ct.c_void_p, ct.c_size_t, _dp, ct.c_double, ct.c_double, _dp,
+                                        ct.POINTER(ct.c_int), _dp]),
 }
 
 
@@ -304,6 +306,17 @@ class Engine:
 
     def grad_end(self):
         self._check(self.L.b200jk_grad_end(self.h))
+
+    def matrix_power(self, A, alpha, cutoff, with_info=False):
+        """Matrix::power (libmints/matrix.cc:2370-2424) on the device; returns the powered matrix (and, with_info, the
+        number of eigenvalues kept and the device milliseconds)."""
+        a = np.ascontiguousarray(A, dtype=np.float64)
+        assert a.ndim == 2 and a.shape[0] == a.shape[1]
+        out = np.empty_like(a)
+        kept, ms = ct.c_int(), ct.c_double()
+        self._check(self.L.b200jk_matrix_power(self.h, a.shape[0], _d(a), float(alpha), float(cutoff), _d(out),
+                                               ct.byref(kept), ct.byref(ms)))
+        return (out, kept.value, ms.value) if with_info else out
 
     def stats(self) -> dict:
         s = Stats()

@@ -40,7 +40,10 @@ class DFTensors:
     """Host part of DFHelper::initialize for the in-core STORE method (dfhelper.cc:149-215, :514-588)."""
 
     def __init__(self, mol: Molecule, primary: BasisSet, aux: BasisSet, cutoff: float = 1e-12, condition: float = 1e-10,
-                 do_wK: bool = False, fit_on_device: bool = False, omega: float = 0.0):
+                 do_wK: bool = False, fit_on_device: bool = False, omega: float = 0.0, power=None):
+        """power(A, alpha, cutoff): Matrix::power implementation; default the host one (numpy), the engine-backed JK
+        passes the device one (b200jk_matrix_power)."""
+        matrix_power_ = power or matrix_power
         if do_wK and not omega > 0.0:
             raise ValueError("do_wK needs omega > 0 (JK::set_omega)")
         mints = MintsHelper(mol, primary)
@@ -51,7 +54,7 @@ class DFTensors:
                                   [aux.shell_nfunction(s) for s in range(aux.nshell())])  # :84-103
         self.dfh.prepare_sparsity(fun_max_vals=mints.schwarz_function_maxima())   # prepare_sparsity :299-420
         metric = mints.metric(aux)                                                 # prepare_metric :1462-1476
-        self.Jm12 = matrix_power(metric, -0.5, condition)                          # compute_metric :1491-1517
+        self.Jm12 = matrix_power_(metric, -0.5, condition)                         # compute_metric :1491-1517
         Amn = mints.three_center(aux)                                              # :1284-1347
         self.Ppq = self.dense = self.m1Ppq = self.wPpq = None
         self.unfitted = None  # tensor id -> (symmetric-packed unfitted integrals, metric power or None)
@@ -59,7 +62,7 @@ class DFTensors:
         if do_wK:
             # prepare_AO_wK_core :589-699 -- m1Ppq_ = J^-1 (A|mn) (wmpower_ = -1.0), wPpq_ = (A|erf(omega r)/r|mn) unfitted
             self.dfh.set_do_wK(True)
-            Jm1 = matrix_power(metric, -1.0, condition)
+            Jm1 = matrix_power_(metric, -1.0, condition)
             Wmn = mints.three_center(aux, omega)
         if fit_on_device:
             # hand the unfitted n >= m half to the engine (b200jk_fit_rows); metric contraction + mirror run on the GPU.
@@ -97,8 +100,9 @@ def build_jk(mol: Molecule, primary: BasisSet, aux: BasisSet, *, cutoff: float =
         jk = jk_factory(t.dfh, t.Ppq, t.m1Ppq, t.wPpq) if do_wK else jk_factory(t.dfh, t.Ppq)
         jk.mints_ = t.mints
     else:
-        def provider(cutoff, condition, omega, do_wK):
-            return DFTensors(mol, primary, aux, cutoff, condition, do_wK=do_wK, fit_on_device=fit_on_device, omega=omega)
+        def provider(cutoff, condition, omega, do_wK, power=None):
+            return DFTensors(mol, primary, aux, cutoff, condition, do_wK=do_wK, fit_on_device=fit_on_device, omega=omega,
+                             power=power)
 
         # the tables of the build-time cutoff size nbf / memory_estimate(); initialize() rebuilds them from the knobs
         dfh = DFHelper(primary.nbf(), aux.nbf())

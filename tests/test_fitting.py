@@ -142,3 +142,38 @@ def test_gpu_producers_pipeline_with_reused_block_buffer(oracle, monkeypatch, re
         e.unregister_host(buf)
         e.unregister_host(buf2)
     e.close()
+
+
+@pytest.mark.gpu
+def test_gpu_matrix_power_follows_the_reference_drop_rule():
+    """b200jk_matrix_power = Matrix::power (libmints/matrix.cc:2370-2424) on the device: same result as the host
+    restatement (itself checked against the reference's compiled Matrix::power in test_reference_slice.py) on the real
+    fitting metric of water, the same eigenvalue cut on a spectrum with one direction below it, no cut for positive
+    powers, and the count of eigenvalues kept."""
+    from psi4_b200 import Engine, scf
+    from psi4_b200.integrals import BasisSet, MintsHelper, Molecule
+
+    e = Engine(1)
+    mol = Molecule.from_zmat_h2o(0.96, 104.5)
+    P, A = BasisSet.build(mol, "cc-pvdz"), BasisSet.build(mol, "cc-pvdz-jkfit")
+    metric = MintsHelper(mol, P).metric(A)
+    for alpha in (-0.5, -1.0):  # mpower_ and wmpower_, dfhelper.h:356-357
+        R, kept, ms = e.matrix_power(metric, alpha, 1e-10, with_info=True)
+        assert kept == A.nbf() and ms > 0
+        M = scf.matrix_power(metric, alpha, 1e-10)
+        assert np.abs(R - M).max() < 1e-9 * np.abs(M).max()
+        assert np.abs(R - R.T).max() < 1e-12 * np.abs(M).max()
+    rng = np.random.default_rng(0)
+    n = 300
+    V = np.linalg.qr(rng.standard_normal((n, n)))[0]
+    w = 10.0 ** rng.uniform(-3, 0, n)
+    w[5] = 1e-13 * w.max()
+    S = (V * w) @ V.T
+    S = 0.5 * (S + S.T)
+    R, kept, _ = e.matrix_power(S, -0.5, 1e-10, with_info=True)
+    assert kept == n - 1  # the 1e-13 direction is dropped ...
+    assert np.abs(R - scf.matrix_power(S, -0.5, 1e-10)).max() < 1e-9 * np.abs(R).max()
+    R, kept, _ = e.matrix_power(S, 0.5, 1e-10, with_info=True)
+    assert kept == n  # ... but never for a positive power (matrix.cc:2403)
+    assert np.abs(R - scf.matrix_power(S, 0.5, 1e-10)).max() < 1e-9 * np.abs(R).max()
+    e.close()
