@@ -204,6 +204,8 @@ typedef struct {
     int q_begin, q_end;   /* Q range of local shard 0                              */
     int reduce_kind;      /* cross-GPU sum: 0 none (one GPU), 1 fixed-rank-order peer-memory kernel over NVLink,
                              2 NCCL all-reduce (B200JK_REDUCE=nccl, or no peer access between the devices) */
+    int kgemm_kind;       /* arm the K GEMM took: 0 FP64 tensor pipe (DMMA), 1 INT8 tensor cores by residues       */
+    int kgemm_moduli;     /* moduli of the residue arm (13: 50 bits below the row norm)                            */
 } b200jk_stats;
 
 int b200jk_get_stats(const b200jk_t* h, b200jk_stats* out);
@@ -217,6 +219,17 @@ int b200jk_hbm_estimate(const b200jk_t* h, size_t max_nocc, int do_wK, uint64_t*
  * Stands in for DFHelper::set_memory + Qshell_blocks_for_JK_build (:814-869): smaller budgets
  * make the K build loop over Q chunks. */
 int b200jk_set_work_budget(b200jk_t* h, uint64_t bytes);
+
+/* Arm of the K GEMM  K += T1 T2^T  (the C_DGEMM of DFHelper::compute_K, lib3index/dfhelper.cc:3374).
+ *   arm 0  automatic: the INT8 residue arm from 128 basis functions and 2^24 elements of T on, when its planes fit
+ *   arm 1  FP64 tensor pipe (DMMA m8n8k4, kgemm_ws_kernel)
+ *   arm 2  INT8 tensor cores (tcgen05.mma.kind::i8): the rows of T are scaled to integers of `moduli`-dependent width,
+ *          multiplied exactly modulo `moduli` coprime numbers <= 256 and rebuilt by the Chinese remainder theorem.
+ *          The only rounding is the scaling of T: |dK[m,n]| <= 2^-bits * sqrt(kdim) * |T[m,:]| |T[n,:]| worst case,
+ *          ~2^-bits |T[m,:]| |T[n,:]| observed, bits = 50.7 at 13 moduli (default, = what a DGEMM in double commits),
+ *          46.9 at 12, 43.0 at 11; bit-identical run to run for any split of the work.
+ * moduli: 0 = default (13), else 6..13.  Environment: B200JK_KGEMM=dmma|i8, B200JK_I8_MODULI=n. */
+int b200jk_set_kgemm(b200jk_t* h, int arm, int moduli);
 
 /* ---- synthetic workload support (bench.py / large-size tests only; not in the reference) ------ */
 

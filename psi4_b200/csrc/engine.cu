@@ -28,6 +28,7 @@
 #include "j_kernels.cuh"
 #include "gemm_strided.cuh"
 #include "peer_reduce.cuh"
+#include "i8_kgemm.cuh"
 
 using namespace b2k;
 
@@ -158,6 +159,8 @@ struct Shard {
     uint64_t launches = 0;
     // half transforms skipped in the current build because C_left repeated (Task::same_left): sum of q rows, q rows x nocc
     double skipped_q = 0, skipped_qo = 0;
+    I8Plan i8;        // residue planes / workspace of the INT8-tensor-core K GEMM (i8_kgemm.cuh)
+    int kgemm_kind = 0, kgemm_moduli = 0;  // arm the last K GEMM of the current build took (0 DMMA, 1 INT8 residues)
     int j_reads = 0;  // passes over the tensor the J sweeps of the current build made (first sweeps + batched second sweeps)
 };
 }  // namespace
@@ -178,6 +181,7 @@ struct b200jk {
     std::vector<size_t> cols_off;
     int max_sp = 0;
     uint64_t work_budget = 0;
+    int kgemm_arm = 0, kgemm_nmod = 0;  // b200jk_set_kgemm: 0 automatic / 1 DMMA / 2 INT8 residues; moduli (0 = default)
     double* pin_in = nullptr;
     double* pin_out = nullptr;
     size_t pin_in_cap = 0, pin_out_cap = 0;
@@ -626,7 +630,74 @@ int run_half(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o, i
     }
 }
 
+// Which arm the K GEMM takes.  B200JK_KGEMM=dmma|i8 (or b200jk_set_kgemm) forces one; automatic = the INT8 residue
+// arm from 128 basis functions and 2^24 elements of T on (below that its five launches cost more than the DMMA kernel).
+int kgemm_want_i8(const b200jk* h, int kdim) {
+    static int env = -1;
+    if (env < 0) {
+        const char* e = getenv("B200JK_KGEMM");
+        env = !e ? 0 : (!strcmp(e, "dmma") ? 1 : (!strcmp(e, "i8") ? 2 : 0));
+    }
+    const int arm = h->kgemm_arm ? h->kgemm_arm : env;
+    if (arm == 1 || use_legacy()) return 0;
+    if (arm == 2) return 1;
+    return h->nbf >= 128 && kdim >= 4096 && (size_t)h->nbf * (size_t)kdim >= ((size_t)1 << 24);
+}
+int kgemm_moduli(const b200jk* h) {
+    static int env = -1;
+    if (env < 0) {
+        const char* e = getenv("B200JK_I8_MODULI");
+        env = e ? atoi(e) : 0;
+    }
+    const int n = h->kgemm_nmod ? h->kgemm_nmod : (env ? env : I8_MAXMOD);
+    return std::max(I8_MINMOD, std::min(I8_MAXMOD, n));
+}
+
+// K4 on the INT8 tensor cores (i8_kgemm.cuh).  Returns -1 when the residue planes do not fit in what is free right
+// now (the caller then takes the DMMA arm: slower, never wrong).
+int run_kgemm_i8(b200jk* h, Shard& s, const double* T1, const double* T2, int kdim, bool symmetric, double* Kout) {
+    static int klen_env = -1;
+    if (klen_env < 0) {
+        const char* e = getenv("B200JK_I8_KLEN");
+        klen_env = e ? atoi(e) : 0;
+    }
+    const int nmod = kgemm_moduli(h);
+    const int klen = klen_env > 0 ? klen_env : 8192;
+    const int nbf = (int)h->nbf, nop = symmetric ? 1 : 2;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const size_t held = s.i8.planes_cap[0] + s.i8.planes_cap[1] + s.i8.ws_cap;
+    const size_t ntile_est = (size_t)((nbf + I8_TM - 1) / I8_TM) * ((nbf + I8_TN - 1) / I8_TN + 1);
+    const size_t ws_est = ((size_t)(kdim + klen - 1) / klen) * nmod * ntile_est * I8_TILE_BYTES;
+    const size_t reserve = (size_t)1 << 30;
+    const size_t avail = free_b + held;
+    const size_t min_planes = (size_t)nmod * nbf * nop * (size_t)std::min(kdim, 4 * klen);
+    if (avail < ws_est + reserve + min_planes) return -1;
+    const size_t budget = avail - ws_est - reserve;
+    std::string err;
+    I8RunInfo info;
+    const uint64_t l0 = s.i8.launches;
+    int rc = i8_kgemm_run(s.i8, (I8EncodeFn)g_encode, s.stream, s.nsm, T1, T2, (size_t)kdim, nbf, kdim, symmetric, Kout, nbf, nmod,
+                          klen, budget, &info, &err);
+    s.launches += s.i8.launches - l0;
+    if (rc == 3) {  // lost a race for the memory: release and let the DMMA arm run
+        cudaGetLastError();
+        s.i8.release();
+        return -1;
+    }
+    if (rc) return fail(h, B200JK_ERR_CUDA, "INT8 K GEMM: %s", err.c_str());
+    s.kgemm_kind = 1;
+    s.kgemm_moduli = info.nmod;
+    return 0;
+}
+
 int run_kgemm(b200jk* h, Shard& s, const double* T1, const double* T2, int kdim, bool symmetric, double* Kout) {
+    if (kgemm_want_i8(h, kdim)) {
+        int rc = run_kgemm_i8(h, s, T1, T2, kdim, symmetric, Kout);
+        if (rc >= 0) return rc;
+    }
+    s.kgemm_kind = 0;
+    s.kgemm_moduli = 0;
     if (!use_legacy()) return run_kgemm_ws(h, s, T1, T2, kdim, symmetric, Kout);
     static bool attr_set[64] = {false};
     constexpr size_t smem = gemm_smem_bytes<8>();
@@ -1126,6 +1197,7 @@ void free_shard(Shard& s) {
                     s.Ctl,       s.Ctr,   s.dpart, s.T1,  s.T2,     s.ws};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    s.i8.release();
     for (auto e : s.evpool) cudaEventDestroy(e);
     for (auto e : s.fit_raw_free)
         if (e) cudaEventDestroy(e);
@@ -1555,6 +1627,13 @@ int b200jk_set_work_budget(b200jk_t* h, uint64_t bytes) {
     return 0;
 }
 
+int b200jk_set_kgemm(b200jk_t* h, int arm, int moduli) {
+    if (!h || arm < 0 || arm > 2 || (moduli && (moduli < I8_MINMOD || moduli > I8_MAXMOD))) return B200JK_ERR_INVALID;
+    h->kgemm_arm = arm;
+    h->kgemm_nmod = moduli;
+    return 0;
+}
+
 int b200jk_hbm_estimate(const b200jk_t* h, size_t max_nocc, int do_wK, uint64_t* bytes_per_gpu) {
     if (!h || !bytes_per_gpu) return B200JK_ERR_INVALID;
     if (!h->have_layout) return B200JK_ERR_INVALID;
@@ -1843,7 +1922,10 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
     {
         Shard& s = h->sh[0];
         h->stats.hbm_work_bytes =
-            8 * (s.in_cap + s.out_cap + 2 * s.ct_cap + s.dpart_cap + s.T_cap + s.T2_cap + s.ws_cap + s.cg_cap);
+            8 * (s.in_cap + s.out_cap + 2 * s.ct_cap + s.dpart_cap + s.T_cap + s.T2_cap + s.ws_cap + s.cg_cap) +
+            s.i8.planes_cap[0] + s.i8.planes_cap[1] + s.i8.ws_cap;
+        h->stats.kgemm_kind = s.kgemm_kind;
+        h->stats.kgemm_moduli = s.kgemm_moduli;
     }
     return 0;
 }
