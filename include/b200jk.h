@@ -206,6 +206,7 @@ typedef struct {
                              2 NCCL all-reduce (B200JK_REDUCE=nccl, or no peer access between the devices) */
     int kgemm_kind;       /* arm the K GEMM took: 0 FP64 tensor pipe (DMMA), 1 INT8 tensor cores by residues       */
     int kgemm_moduli;     /* moduli of the residue arm (13: 50 bits below the row norm)                            */
+    int half_kind;        /* arm the half transform took: 0 FP64 tensor pipe (DMMA), 1 INT8 tensor cores by residues */
 } b200jk_stats;
 
 int b200jk_get_stats(const b200jk_t* h, b200jk_stats* out);
@@ -230,6 +231,14 @@ int b200jk_set_work_budget(b200jk_t* h, uint64_t bytes);
  *          46.9 at 12, 43.0 at 11; bit-identical run to run for any split of the work.
  * moduli: 0 = default (13), else 6..13.  Environment: B200JK_KGEMM=dmma|i8, B200JK_I8_MODULI=n. */
 int b200jk_set_kgemm(b200jk_t* h, int arm, int moduli);
+
+/* The same choice for the half transform  T[m,Q,i] = sum_n B[Q,m,n] C[n,i]  (DFHelper::first_transform_pQq,
+ * lib3index/dfhelper.cc:2162-2186): arm 0 automatic, 1 FP64 tensor pipe (half_ws_kernel), 2 INT8 tensor cores.  The
+ * residue arm scales every row (m,Q) of the resident tensor (once per tensor) and every column of C (once per build) to
+ * integers, multiplies modulo `moduli` coprime numbers (default 12: 46.9 bits below |B[Q,m,:]| |C[:,i]|) and rebuilds T
+ * by the Chinese remainder theorem.  The first J sweep rides on the conversion of the tensor rows instead of on the GEMM.
+ * Environment: B200JK_HALF=dmma|i8, B200JK_I8_HALF_MODULI=n, B200JK_I8_CLUSTER=1|2|4. */
+int b200jk_set_half(b200jk_t* h, int arm, int moduli);
 
 /* ---- synthetic workload support (bench.py / large-size tests only; not in the reference) ------ */
 

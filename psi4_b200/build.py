@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200jk.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["dmma_gemm.cuh", "dmma_ws.cuh", "i8_kgemm.cuh", "fit_kernels.cuh", "fit_host.inl", "j_kernels.cuh", "aux_kernels.cuh", "peer_reduce.cuh", "peer_host.inl", "gemm_strided.cuh", "grad_host.inl", "power_host.inl", os.path.join("..", "..", "include", "b200jk.h")]
+HEADERS = ["dmma_gemm.cuh", "dmma_ws.cuh", "i8_kgemm.cuh", "i8_half.cuh", "fit_kernels.cuh", "fit_host.inl", "j_kernels.cuh", "aux_kernels.cuh", "peer_reduce.cuh", "peer_host.inl", "gemm_strided.cuh", "grad_host.inl", "power_host.inl", os.path.join("..", "..", "include", "b200jk.h")]
 
 
 def _stale() -> bool:

@@ -29,6 +29,7 @@
 #include "gemm_strided.cuh"
 #include "peer_reduce.cuh"
 #include "i8_kgemm.cuh"
+#include "i8_half.cuh"
 
 using namespace b2k;
 
@@ -160,6 +161,8 @@ struct Shard {
     // half transforms skipped in the current build because C_left repeated (Task::same_left): sum of q rows, q rows x nocc
     double skipped_q = 0, skipped_qo = 0;
     I8Plan i8;        // residue planes / workspace of the INT8-tensor-core K GEMM (i8_kgemm.cuh)
+    I8HalfPlan i8h;   // row scales, C planes and scratch arena of the INT8-tensor-core half transform (i8_half.cuh)
+    int half_kind = 0;  // arm the last half transform of the current build took (0 DMMA, 1 INT8 residues)
     int kgemm_kind = 0, kgemm_moduli = 0;  // arm the last K GEMM of the current build took (0 DMMA, 1 INT8 residues)
     int j_reads = 0;  // passes over the tensor the J sweeps of the current build made (first sweeps + batched second sweeps)
 };
@@ -182,6 +185,7 @@ struct b200jk {
     int max_sp = 0;
     uint64_t work_budget = 0;
     int kgemm_arm = 0, kgemm_nmod = 0;  // b200jk_set_kgemm: 0 automatic / 1 DMMA / 2 INT8 residues; moduli (0 = default)
+    int half_arm = 0, half_nmod = 0;    // b200jk_set_half: the same for the half transform
     double* pin_in = nullptr;
     double* pin_out = nullptr;
     size_t pin_in_cap = 0, pin_out_cap = 0;
@@ -593,9 +597,92 @@ int launch_half(b200jk* h, Shard& s, const HalfParams& p, dim3 grid) {
     return 0;
 }
 
+int kgemm_want_i8(const b200jk* h, int kdim);
+int kgemm_moduli(const b200jk* h);
+
+// Which arm the half transform takes.  B200JK_HALF=dmma|i8 (or b200jk_set_half) forces one.
+int half_want_i8(const b200jk* h, const Shard& s, int o) {
+    static int env = -1;
+    if (env < 0) {
+        const char* e = getenv("B200JK_HALF");
+        env = !e ? 0 : (!strcmp(e, "dmma") ? 1 : (!strcmp(e, "i8") ? 2 : 0));
+    }
+    const int arm = h->half_arm ? h->half_arm : env;
+    if (arm == 1 || use_legacy() || o <= 0) return 0;
+    if (arm == 2) return 1;
+    return 0;  // automatic: the DMMA arm
+}
+int half_moduli(const b200jk* h) {
+    static int env = -1;
+    if (env < 0) {
+        const char* e = getenv("B200JK_I8_HALF_MODULI");
+        env = e ? atoi(e) : 0;
+    }
+    const int n = h->half_nmod ? h->half_nmod : (env ? env : 12);
+    return std::max(I8_MINMOD, std::min(I8_MAXMOD, n));
+}
+
+// K3 on the INT8 tensor cores (i8_half.cuh).  Returns -1 when no scratch arena can be had (the caller then takes the
+// DMMA arm).  max_o: the largest nocc of the build.
+int run_half_i8(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o, int op, int max_o, int qbeg, int qc, double* T,
+                const FuseJ* fj) {
+    static int cl_env = -1;
+    if (cl_env < 0) {
+        const char* e = getenv("B200JK_I8_CLUSTER");
+        cl_env = e ? atoi(e) : 2;
+    }
+    const int nmod = half_moduli(h), cluster = cl_env;
+    const int nbf = (int)h->nbf;
+    size_t mn = 0, all = 0;
+    i8h_arena_need(s.i8h, nmod, qc, max_o, cluster, &mn, &all);
+    if (s.i8h.arena_cap < mn || (s.i8h.arena_cap < all && s.i8h.arena_cap < ((size_t)8 << 30))) {
+        // (re)size the arena: everything in one chunk if it fits beside what the K GEMM's residue arm will ask for
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        size_t avail = free_b + s.i8h.arena_cap;
+        size_t k4 = 0;
+        if (kgemm_want_i8(h, qc * op) && !s.i8.planes_cap[0])
+            k4 = (size_t)kgemm_moduli(h) * nbf * ((size_t)qc * op + 128) * 2 + ((size_t)3 << 30);
+        const size_t reserve = (size_t)2 << 30;
+        if (avail < k4 + reserve + mn) return -1;
+        const size_t want = std::min(all, avail - k4 - reserve);
+        if (want > s.i8h.arena_cap) {
+            s.i8h.release_arena();
+            if (cudaMalloc((void**)&s.i8h.arena, want) != cudaSuccess) {
+                cudaGetLastError();
+                s.i8h.arena = nullptr;
+                return -1;
+            }
+            s.i8h.arena_cap = want;
+        }
+    }
+    std::string err;
+    I8HalfInfo info;
+    I8HalfFuseJ f8 = {nullptr, 0, nullptr, 0, nullptr, nullptr};
+    if (fj) {  // the first J sweep rides on the conversion (the DMMA arm carries it as an extra operand row instead)
+        f8.Dm = fj->Dm;
+        f8.ldd = fj->ldd;
+        f8.dpart = fj->dpart;
+        f8.dstride = fj->dstride;
+    }
+    const uint64_t l0 = s.i8h.launches;
+    int rc = i8_half_run(s.i8h, s.stream, s.nsm, s.tensor[which], which, s.d_row_off, s.d_ldm, s.d_sp, s.d_cols, s.d_cols_off, nbf, s.nq,
+                         Ct, ldc, o, op, max_o, qbeg, qc, T, (size_t)qc * op, nmod, cluster, fj ? &f8 : nullptr, &info, &err);
+    s.launches += s.i8h.launches - l0;
+    if (rc == 3) return -1;
+    if (rc) return fail(h, B200JK_ERR_CUDA, "INT8 half transform: %s", err.c_str());
+    s.half_kind = 1;
+    return 0;
+}
+
 // T[m][q][i] for q in the chunk [qbeg, qbeg+qc): one launch over (i-tiles, q-tiles, m).
 int run_half(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o, int op, int qbeg, int qc, double* T,
-             const FuseJ* fj = nullptr) {
+             const FuseJ* fj = nullptr, int max_o = 0) {
+    if (half_want_i8(h, s, o)) {
+        int rc = run_half_i8(h, s, which, Ct, ldc, o, op, std::max(max_o, o), qbeg, qc, T, fj);
+        if (rc >= 0) return rc;
+    }
+    s.half_kind = 0;
     if (!use_legacy()) return run_half_ws(h, s, which, Ct, ldc, o, op, qbeg, qc, T, fj);
     const double* tensor = s.tensor[which];
     int nit = (o + 127) / 128;
@@ -683,6 +770,7 @@ int run_kgemm_i8(b200jk* h, Shard& s, const double* T1, const double* T2, int kd
     if (rc == 3) {  // lost a race for the memory: release and let the DMMA arm run
         cudaGetLastError();
         s.i8.release();
+    s.i8h.release();
         return -1;
     }
     if (rc) return fail(h, B200JK_ERR_CUDA, "INT8 K GEMM: %s", err.c_str());
@@ -985,11 +1073,11 @@ int run_device_K(b200jk* h, Shard& s, const Task& t, const double* const* dCl, c
                     if (reuse_T1) {
                         s.skipped_q += nqc;
                         s.skipped_qo += (double)nqc * o;
-                    } else if ((rc = run_half(h, s, tenL, s.Ctl, ldc, o, op, qb, nqc, s.T1, fj))) {
+                    } else if ((rc = run_half(h, s, tenL, s.Ctl, ldc, o, op, qb, nqc, s.T1, fj, t.max_o))) {
                         return rc;
                     }
                     FuseJ* fj2 = reuse_T1 ? fj : nullptr;
-                    if (!one_T && (rc = run_half(h, s, tenR, s.Ctr, ldc, o, op, qb, nqc, s.T2, fj2))) return rc;
+                    if (!one_T && (rc = run_half(h, s, tenR, s.Ctr, ldc, o, op, qb, nqc, s.T2, fj2, t.max_o))) return rc;
                 }
                 {
                     PhaseScope ps(s, 2);
@@ -1453,6 +1541,10 @@ int b200jk_set_layout(b200jk_t* h, size_t nbf, size_t naux, const size_t* small_
         if ((rc = upload_vec(h, &s.d_cols_off, h->cols_off))) return rc;
         if ((rc = upload_vec(h, &s.d_mpos, h->mpos))) return rc;
         {
+            std::string e8;
+            if (i8h_set_layout(s.i8h, h->sp, &e8)) return fail(h, B200JK_ERR_CUDA, "INT8 half transform layout: %s", e8.c_str());
+        }
+        {
             // K-GEMM tile lists sorted by live area (rows x cols inside nbf), largest first
             const int n1d = ((int)nbf + BM - 1) / BM;
             auto live = [&](int t) { return std::min<int>(BM, (int)nbf - t * BM); };
@@ -1557,6 +1649,7 @@ int b200jk_upload_rows(b200jk_t* h, int which, size_t m0, size_t m1, const doubl
                 m0, m1, total_bytes / 1e6, direct ? "direct" : "staged", now_s() - t_call, h->stage_wait_s, h->stage_alloc_s,
                 h->stage_copy_s, now_s() - ts);
     if (m1 == h->nbf) h->uploaded[which] = true;  // streaming: the last block completes the tensor
+    for (auto& s : h->sh) s.i8h.expo_valid[which] = false;  // the row scales of the INT8 half transform follow the tensor
     h->stats.hbm_tensor_bytes = 0;
     for (int w = 0; w < 3; w++)
         if (h->sh[0].tensor[w]) h->stats.hbm_tensor_bytes += h->sh[0].tensor_doubles * 8;
@@ -1589,6 +1682,7 @@ int b200jk_fill_synthetic(b200jk_t* h, int which, uint64_t seed, const double* a
         CK(cudaFree(damp));
     }
     h->uploaded[which] = true;
+    for (auto& s : h->sh) s.i8h.expo_valid[which] = false;
     h->stats.hbm_tensor_bytes = 0;
     for (int w = 0; w < 3; w++)
         if (h->sh[0].tensor[w]) h->stats.hbm_tensor_bytes += h->sh[0].tensor_doubles * 8;
@@ -1631,6 +1725,15 @@ int b200jk_set_kgemm(b200jk_t* h, int arm, int moduli) {
     if (!h || arm < 0 || arm > 2 || (moduli && (moduli < I8_MINMOD || moduli > I8_MAXMOD))) return B200JK_ERR_INVALID;
     h->kgemm_arm = arm;
     h->kgemm_nmod = moduli;
+    return 0;
+}
+
+int b200jk_set_half(b200jk_t* h, int arm, int moduli) {
+    if (!h || arm < 0 || arm > 2 || (moduli && (moduli < I8_MINMOD || moduli > I8_MAXMOD))) return B200JK_ERR_INVALID;
+    h->half_arm = arm;
+    h->half_nmod = moduli;
+    for (auto& s : h->sh)
+        for (int w = 0; w < 3; w++) s.i8h.expo_valid[w] = s.i8h.expo_valid[w] && (moduli == 0 || s.i8h.expo_nmod[w] == moduli);
     return 0;
 }
 
@@ -1925,6 +2028,8 @@ static int compute_impl(b200jk_t* h, bool host_ops, int nmat, const double* cons
             8 * (s.in_cap + s.out_cap + 2 * s.ct_cap + s.dpart_cap + s.T_cap + s.T2_cap + s.ws_cap + s.cg_cap) +
             s.i8.planes_cap[0] + s.i8.planes_cap[1] + s.i8.ws_cap;
         h->stats.kgemm_kind = s.kgemm_kind;
+        h->stats.half_kind = s.half_kind;
+        h->stats.hbm_work_bytes += s.i8h.arena_cap;
         h->stats.kgemm_moduli = s.kgemm_moduli;
     }
     return 0;

@@ -205,6 +205,8 @@ extern "C" int b200jk_set_metric(b200jk_t* h, const double* metric) {
 }
 
 extern "C" int b200jk_fit_rows(b200jk_t* h, int which, size_t m0, size_t m1, const double* host_sym) {
+    if (h && which >= 0 && which <= 2)
+        for (auto& sh : h->sh) sh.i8h.expo_valid[which] = false;  // the row scales of the INT8 half transform follow the tensor
     if (!h) return B200JK_ERR_INVALID;
     if (!h->have_layout) return fail(h, B200JK_ERR_INVALID, "fit_rows before set_layout");
     if (which < 0 || which > 2 || m0 > m1 || m1 > h->nbf || !host_sym) return fail(h, B200JK_ERR_INVALID, "bad fit_rows args");

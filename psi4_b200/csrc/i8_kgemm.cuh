@@ -59,6 +59,16 @@ struct I8Consts {
 };
 __constant__ I8Consts c_i8;
 
+// Constants of the floating-point CRT for one number of moduli (i8_crt_value_fast): value / M = frac(sum_j r_j q_j / p_j),
+// q_j = (M / p_j)^-1 mod p_j as a symmetric representative; 1 / p_j = ih_j + il_j with ih_j a multiple of 2^-32.
+struct I8CrtFast {
+    int q[16];
+    double ih[16], il[16];
+    double Md;
+    int nmod;
+};
+__constant__ I8CrtFast c_i8f;
+
 struct I8Tile {
     int row0, col0, ncols, bmap;  // rows [row0, row0+128) of T1 against rows [col0, col0+ncols) of T2; which B map
 };
@@ -135,9 +145,48 @@ __device__ __forceinline__ uint32_t i8_pack4(const uint32_t* v, uint32_t p, uint
 }
 
 // ---- step 3: residue GEMM --------------------------------------------------------------------------------
+// One work item of the persistent pipeline: D[128 x ncols] (int32, TMEM) = A[128 x K] B[ncols x K]^T for one modulus,
+// K = nkb blocks of 128 bytes; the accumulator is reduced mod p and stored as bytes, `rows` rows of `ncols` bytes.
+struct I8Item {
+    const CUtensorMap *amap, *bmap;
+    int ax, ay, az, bx, by, bz;  // TMA coordinates of k-block 0 (x advances by 128 per k-block)
+    int nkb, ncols, mod, rows;
+    uint8_t* dst;      // residues of row 0
+    size_t dst_pitch;  // bytes between rows
+};
+
+// The K GEMM's items: (k-range, modulus, tile) in that order.
+struct I8KgemmTraits {
+    typedef I8GemmParams Params;
+    static __device__ __forceinline__ int nitems(const Params& p) { return p.nitems; }
+    static __device__ __forceinline__ int* counter(const Params& p) { return p.counter; }
+    static __device__ __forceinline__ void decode(const Params& p, int it, const CUtensorMap* amap, const CUtensorMap* b0,
+                                                  const CUtensorMap* b1, const CUtensorMap* b2, I8Item& x) {
+        const int per_split = p.nmod * p.ntile;
+        const int split = it / per_split, rem = it - split * per_split;
+        const int mod = rem / p.ntile, tile = rem - mod * p.ntile;
+        const I8Tile t = p.tiles[tile];
+        const int k0 = split * p.klen;
+        x.amap = amap;
+        x.bmap = t.bmap == 0 ? b0 : (t.bmap == 1 ? b1 : b2);
+        x.ax = x.bx = k0;
+        x.ay = t.row0;
+        x.by = t.col0;
+        x.az = x.bz = mod;
+        x.nkb = (min(p.klen, p.kdim - k0) + I8_BK - 1) / I8_BK;
+        x.ncols = t.ncols;
+        x.mod = mod;
+        x.rows = I8_TM;
+        x.dst = p.ws + (size_t)it * I8_TILE_BYTES;
+        x.dst_pitch = I8_TN;
+    }
+};
+
+template <class Traits>
 __global__ void __launch_bounds__(I8_THREADS, 1)
-i8_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap0,
-               const __grid_constant__ CUtensorMap bmap1, const __grid_constant__ CUtensorMap bmap2, const I8GemmParams p) {
+i8_pipeline_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap0,
+                   const __grid_constant__ CUtensorMap bmap1, const __grid_constant__ CUtensorMap bmap2,
+                   const typename Traits::Params p) {
     extern __shared__ uint8_t i8_raw[];
     uint8_t* base = i8_raw + ((1024u - (smem_u32(i8_raw) & 1023u)) & 1023u);
     uint8_t* As = base;
@@ -174,7 +223,7 @@ i8_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const int per_split = p.nmod * p.ntile;
+    const int nitems = Traits::nitems(p);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -183,29 +232,25 @@ i8_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
             uint32_t stage = 0, phase = 0, qs = 0, qph = 0;
             for (;;) {
                 // dynamic queue: the CTAs take the items in their global order, so the ~148 items in flight always
-                // belong to two or three neighbouring (k-range, modulus) slabs and those stay in L2 (a static
-                // round-robin lets the CTAs drift apart over ~600 items each: 27.9 -> ms at C60)
-                const int it = atomicAdd(p.counter, 1);
+                // belong to neighbouring slabs of the operands and those stay in L2 (a static round-robin lets the
+                // CTAs drift apart over ~600 items each: 27.9 ms instead of 16.6 for the C60 K GEMM)
+                const int it = atomicAdd(Traits::counter(p), 1);
                 mbar_wait(&qempty[qs], qph ^ 1);
-                qitem[qs] = it < p.nitems ? it : -1;
+                qitem[qs] = it < nitems ? it : -1;
                 mbar_arrive(&qfull[qs]);
                 if (++qs == I8_QRING) {
                     qs = 0;
                     qph ^= 1;
                 }
-                if (it >= p.nitems) break;
-                const int split = it / per_split, rem = it - split * per_split;
-                const int mod = rem / p.ntile, tile = rem - mod * p.ntile;
-                const I8Tile t = p.tiles[tile];
-                const CUtensorMap* bm = t.bmap == 0 ? &bmap0 : (t.bmap == 1 ? &bmap1 : &bmap2);
-                const uint32_t bytes = I8_A_STAGE + (uint32_t)t.ncols * I8_BK;
-                const int k0 = split * p.klen;
-                const int nkb = (min(p.klen, p.kdim - k0) + I8_BK - 1) / I8_BK;
-                for (int kb = 0; kb < nkb; kb++) {
+                if (it >= nitems) break;
+                I8Item x;
+                Traits::decode(p, it, &amap, &bmap0, &bmap1, &bmap2, x);
+                const uint32_t bytes = I8_A_STAGE + (uint32_t)x.ncols * I8_BK;
+                for (int kb = 0; kb < x.nkb; kb++) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full[stage], bytes);
-                    tma_load_3d(As + stage * I8_A_STAGE, &amap, k0 + kb * I8_BK, t.row0, mod, &full[stage]);
-                    tma_load_3d(Bs + stage * I8_B_STAGE, bm, k0 + kb * I8_BK, t.col0, mod, &full[stage]);
+                    tma_load_3d(As + stage * I8_A_STAGE, x.amap, x.ax + kb * I8_BK, x.ay, x.az, &full[stage]);
+                    tma_load_3d(Bs + stage * I8_B_STAGE, x.bmap, x.bx + kb * I8_BK, x.by, x.bz, &full[stage]);
                     if (++stage == I8_STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -225,17 +270,14 @@ i8_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
                     qph ^= 1;
                 }
                 if (it < 0) break;
-                const int split = it / per_split, rem = it - split * per_split;
-                const int tile = rem % p.ntile;
-                const I8Tile t = p.tiles[tile];
-                const int k0 = split * p.klen;
-                const int nkb = (min(p.klen, p.kdim - k0) + I8_BK - 1) / I8_BK;
+                I8Item x;
+                Traits::decode(p, it, &amap, &bmap0, &bmap1, &bmap2, x);
                 // instruction descriptor: D = s32, A = B = s8, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-                const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(t.ncols >> 3) << 17) | ((128u >> 4) << 24);
+                const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(x.ncols >> 3) << 17) | ((128u >> 4) << 24);
                 mbar_wait(&tempty[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t dcol = tmem + as * I8_TN;
-                for (int kb = 0; kb < nkb; kb++) {
+                for (int kb = 0; kb < x.nkb; kb++) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint64_t ad = i8_smem_desc(smem_u32(As + stage * I8_A_STAGE));
@@ -266,14 +308,16 @@ i8_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
                 qph ^= 1;
             }
             if (it < 0) break;
-            const int rem = it % per_split;
-            const int mod = rem / p.ntile, tile = rem - mod * p.ntile;
-            const int ncols = p.tiles[tile].ncols;
-            const uint32_t pm = (uint32_t)c_i8.p[mod], magic = c_i8.magic[mod], off = c_i8.off[mod];
+            I8Item x;
+            Traits::decode(p, it, &amap, &bmap0, &bmap1, &bmap2, x);
+            const int ncols = x.ncols;
+            const uint32_t pm = (uint32_t)c_i8.p[x.mod], magic = c_i8.magic[x.mod], off = c_i8.off[x.mod];
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)lane_base << 16) + as * I8_TN;
-            uint8_t* dst = p.ws + (size_t)it * I8_TILE_BYTES + (size_t)(lane_base + lane) * I8_TN;
+            const int row = lane_base + lane;
+            const bool live = row < x.rows;
+            uint8_t* dst = x.dst + (size_t)row * x.dst_pitch;
             uint32_t v[32];
             int c0 = 0;
             for (; c0 + 32 <= ncols; c0 += 32) {
@@ -287,8 +331,10 @@ i8_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
                 w1.y = i8_pack4(v + 20, pm, magic, off);
                 w1.z = i8_pack4(v + 24, pm, magic, off);
                 w1.w = i8_pack4(v + 28, pm, magic, off);
-                *reinterpret_cast<uint4*>(dst + c0) = w0;
-                *reinterpret_cast<uint4*>(dst + c0 + 16) = w1;
+                if (live) {
+                    *reinterpret_cast<uint4*>(dst + c0) = w0;
+                    *reinterpret_cast<uint4*>(dst + c0 + 16) = w1;
+                }
             }
             if (c0 < ncols) {  // ncols is a multiple of 16
                 tmem_ld16(taddr + c0, v);
@@ -297,7 +343,7 @@ i8_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
                 w0.y = i8_pack4(v + 4, pm, magic, off);
                 w0.z = i8_pack4(v + 8, pm, magic, off);
                 w0.w = i8_pack4(v + 12, pm, magic, off);
-                *reinterpret_cast<uint4*>(dst + c0) = w0;
+                if (live) *reinterpret_cast<uint4*>(dst + c0) = w0;
             }
             tc_fence_before();
             __syncwarp();
@@ -309,6 +355,11 @@ i8_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// low bytes of four words -> one word
+__device__ __forceinline__ uint32_t i8_pack_bytes(int a, int b, int c, int d) {
+    return __byte_perm(__byte_perm((uint32_t)a, (uint32_t)b, 0x0040), __byte_perm((uint32_t)c, (uint32_t)d, 0x0040), 0x5410);
 }
 
 // ---- step 1: row norms and scales ------------------------------------------------------------------------
@@ -379,31 +430,28 @@ __global__ void __launch_bounds__(256) i8_convert_kernel(const double* __restric
 #pragma unroll
         for (int c = 0; c < 4; c++) y[c] = (k + c < kdim) ? r[c] : 0.0;
     }
-    // Rounding and the integer residues run on the FP64 FMA pipe alone: (v + 1.5*2^52) - 1.5*2^52 = rint(v) for |v| < 2^51
-    // and the low word of (r + 1.5*2^52) is r in two's complement (FRND/F2I.F64 go through the slow conversion pipe:
-    // 14.2 -> ms for the C60 planes)
+    // Rounding runs on the FP64 FMA pipe alone: (v + 1.5*2^52) - 1.5*2^52 = rint(v) for |v| < 2^51, and the low word of
+    // (v + 1.5*2^52) is v mod 2^32 in two's complement (FRND/F2I.F64 go through the slow conversion pipe).  Per modulus
+    // only q = rint(y / p) needs FP64 (one FMA): r = y - p q lies in [-127, 127], so its byte is (y - p q) mod 256 and
+    // comes from the low words of y and q with one integer multiply-add (46 -> 14 FP64 operations per element).
     const double CM = 6755399441055744.0;
     const double scale = ldexp(1.0, e[row]);
-#pragma unroll
-    for (int c = 0; c < 4; c++) y[c] = __dadd_rn(__fma_rn(y[c], scale, CM), -CM);  // |y| <= 2^51: exact integers
     int8_t* dst = planes + (size_t)row * ldk + k;
-    {
-        uint32_t w = 0;
+    int ylo[4];
 #pragma unroll
-        for (int c = 0; c < 4; c++) w |= ((uint32_t)__double2loint(__dadd_rn(y[c], CM)) & 255u) << (8 * c);  // p = 256: the low byte
-        *reinterpret_cast<uint32_t*>(dst) = w;
+    for (int c = 0; c < 4; c++) {
+        y[c] = __dadd_rn(__fma_rn(y[c], scale, CM), -CM);  // |y| <= 2^51: exact integers
+        ylo[c] = __double2loint(__dadd_rn(y[c], CM));
     }
+    *reinterpret_cast<uint32_t*>(dst) = i8_pack_bytes(ylo[0], ylo[1], ylo[2], ylo[3]);  // p = 256: the low byte
 #pragma unroll
     for (int j = 1; j < NMOD; j++) {
-        const double pj = (double)c_i8.p[j], inv = c_i8.invpd[j];
-        uint32_t w = 0;
+        const int pj = c_i8.p[j];
+        const double inv = c_i8.invpd[j];
+        int r[4];
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const double q = __dadd_rn(__fma_rn(y[c], inv, CM), -CM);
-            const double rr = __fma_rn(-pj, q, y[c]);  // exact, |rr| <= (p-1)/2
-            w |= ((uint32_t)__double2loint(__dadd_rn(rr, CM)) & 255u) << (8 * c);
-        }
-        *reinterpret_cast<uint32_t*>(dst + (size_t)j * plane_stride) = w;
+        for (int c = 0; c < 4; c++) r[c] = ylo[c] - pj * __double2loint(__fma_rn(y[c], inv, CM));
+        *reinterpret_cast<uint32_t*>(dst + (size_t)j * plane_stride) = i8_pack_bytes(r[0], r[1], r[2], r[3]);
     }
 }
 
@@ -423,6 +471,41 @@ __device__ __forceinline__ int i8_modp_small(int t, int p, float invp) {  // 0 <
     if (r < 0) r += p;
     if (r >= p) r -= p;
     return r;
+}
+
+// The integer whose residues (any non-negative representatives < 2^22) are r[0..NMOD): Garner's mixed-radix digits
+// v_j = (..((r_j - v_0) / p_0 - v_1) / p_1 ..) mod p_j, then value = v_0 + p_0 (v_1 + p_1 (v_2 + ...)) in 128 bits, taken
+// in (-M/2, M/2], converted to double (M = product of the moduli, H = M / 2).
+template <int NMOD>
+__device__ __forceinline__ double i8_crt_value(const int (&r)[NMOD], unsigned long long M_lo, unsigned long long M_hi,
+                                               unsigned long long H_lo, unsigned long long H_hi) {
+    int v[NMOD];
+#pragma unroll
+    for (int j = 0; j < NMOD; j++) {
+        const int pj = c_i8.p[j];
+        const float ij = c_i8.invp[j];
+        int x = i8_modp_small(r[j], pj, ij);
+#pragma unroll
+        for (int i = 0; i < j; i++) x = i8_modp_small((x + 2 * pj - v[i]) * c_i8.ginv[i][j], pj, ij);
+        v[j] = x;
+    }
+    unsigned long long lo = (unsigned long long)v[NMOD - 1], hi = 0;
+#pragma unroll
+    for (int j = NMOD - 2; j >= 0; j--) {
+        const unsigned long long pj = (unsigned long long)c_i8.p[j];
+        const unsigned long long l2 = lo * pj;
+        hi = hi * pj + __umul64hi(lo, pj);
+        lo = l2 + (unsigned long long)v[j];
+        if (lo < l2) hi++;
+    }
+    const bool neg = hi > H_hi || (hi == H_hi && lo > H_lo);
+    if (neg) {  // M - value
+        const unsigned long long l2 = M_lo - lo;
+        hi = M_hi - hi - (M_lo < lo ? 1ull : 0ull);
+        lo = l2;
+    }
+    const double d = (double)hi * 18446744073709551616.0 + (double)lo;
+    return neg ? -d : d;
 }
 
 template <int NMOD>
@@ -451,39 +534,38 @@ __global__ void __launch_bounds__(256) i8_crt_kernel(const I8CrtParams p) {
     for (int c = 0; c < 4; c++) {
         const int gn = t.col0 + col4 + c;
         if (gn >= p.nbf || (p.symmetric && gn < gm)) continue;
-        int v[NMOD];
+        int rr[NMOD];
 #pragma unroll
-        for (int j = 0; j < NMOD; j++) {  // Garner: v_j = (..((r_j - v_0) / p_0 - v_1) / p_1 ..) mod p_j
-            const int pj = c_i8.p[j];
-            const float ij = c_i8.invp[j];
-            int x = i8_modp_small(r[j][c], pj, ij);
-#pragma unroll
-            for (int i = 0; i < j; i++) x = i8_modp_small((x + 2 * pj - v[i]) * c_i8.ginv[i][j], pj, ij);
-            v[j] = x;
-        }
-        unsigned long long lo = (unsigned long long)v[NMOD - 1], hi = 0;  // value = v_0 + p_0 (v_1 + p_1 (v_2 + ...))
-#pragma unroll
-        for (int j = NMOD - 2; j >= 0; j--) {
-            const unsigned long long pj = (unsigned long long)c_i8.p[j];
-            const unsigned long long l2 = lo * pj;
-            hi = hi * pj + __umul64hi(lo, pj);
-            lo = l2 + (unsigned long long)v[j];
-            if (lo < l2) hi++;
-        }
-        const bool neg = hi > p.H_hi || (hi == p.H_hi && lo > p.H_lo);
-        if (neg) {  // M - value
-            const unsigned long long l2 = p.M_lo - lo;
-            hi = p.M_hi - hi - (p.M_lo < lo ? 1ull : 0ull);
-            lo = l2;
-        }
-        double d = (double)hi * 18446744073709551616.0 + (double)lo;
-        if (neg) d = -d;
+        for (int j = 0; j < NMOD; j++) rr[j] = r[j][c];
+        const double d = i8_crt_value<NMOD>(rr, p.M_lo, p.M_hi, p.H_lo, p.H_hi);
         const double val = ldexp(d, -(ea + p.eB[gn]));
         double* kp = p.K + (size_t)gm * p.ldK + gn;
         const double nv = *kp + val;
         *kp = nv;
         if (p.symmetric && gn != gm) p.K[(size_t)gn * p.ldK + gm] = nv;
     }
+}
+
+// value = the integer in (-M/2, M/2] with residues r[0..NMOD) (representatives in [0, 256)), as a double good to
+// ~2^-67 M absolute -- four orders of magnitude below the rounding of the operands that produced the residues.  The
+// exact Garner / 128-bit route of i8_crt_value costs ~1000 instructions per element, fine for the nbf^2 elements of K but
+// not for the nbf*naux*nocc elements of the half transform; this one costs ~70: s_j = r_j q_j (|s_j| < 2^15), the high parts
+// s_j ih_j are multiples of 2^-32 below 2^7 and sum exactly in double, the low parts carry the rest.
+template <int NMOD>
+__device__ __forceinline__ double i8_crt_value_fast(const int (&r)[NMOD]) {
+    double fh = 0.0, fl = 0.0;
+#pragma unroll
+    for (int j = 0; j < NMOD; j++) {
+        const int s = r[j] * c_i8f.q[j] + 32768;  // in [0, 65536)
+        const double sd = __hiloint2double(0x43300000, s) - 4503599627403264.0;  // 2^52 + 32768
+        fh = __fma_rn(sd, c_i8f.ih[j], fh);
+        fl = __fma_rn(sd, c_i8f.il[j], fl);
+    }
+    const double CM = 6755399441055744.0;
+    fh -= __dadd_rn(__dadd_rn(fh, CM), -CM);
+    double f = fh + fl;
+    f -= __dadd_rn(__dadd_rn(f, CM), -CM);
+    return f * c_i8f.Md;
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
@@ -551,6 +633,28 @@ inline void i8_fill_consts(I8Consts& c) {
         c.off[i] = (unsigned)((((1u << 30) + (unsigned)p - 1) / (unsigned)p) * (unsigned)p);
         for (int j = 0; j < 16; j++) c.ginv[i][j] = (i < j) ? i8_egcd_inv(p, kI8Moduli[j]) : 0;
     }
+}
+
+inline void i8_fill_crt_fast(I8CrtFast& f, int nmod) {
+    unsigned __int128 M = 1;
+    for (int i = 0; i < nmod; i++) M *= (unsigned)kI8Moduli[i];
+    for (int j = 0; j < 16; j++) {
+        f.q[j] = 0;
+        f.ih[j] = f.il[j] = 0.0;
+    }
+    for (int j = 0; j < nmod; j++) {
+        const int p = kI8Moduli[j];
+        const int mj = (int)((M / (unsigned)p) % (unsigned)p);
+        int q = i8_egcd_inv(mj, p);
+        if (q > p / 2) q -= p;
+        f.q[j] = q;
+        const long double inv = 1.0L / (long double)p;
+        const double ih = (double)(rintl(inv * 4294967296.0L) / 4294967296.0L);
+        f.ih[j] = ih;
+        f.il[j] = (double)(inv - (long double)ih);
+    }
+    f.Md = (double)(long double)M;
+    f.nmod = nmod;
 }
 
 // Rb(nmod, kdim): bound on the 2-norm of a scaled row BEFORE rounding, so that after rounding (each element moves by at
@@ -656,7 +760,7 @@ inline int i8_kgemm_run(I8Plan& pl, I8EncodeFn enc, cudaStream_t st, int nsm, co
     }
     if (!pl.d_counter) I8CK(cudaMalloc((void**)&pl.d_counter, sizeof(int)));
     if (!pl.attr) {
-        I8CK(cudaFuncSetAttribute(i8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)i8_smem_bytes()));
+        I8CK(cudaFuncSetAttribute(i8_pipeline_kernel<I8KgemmTraits>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)i8_smem_bytes()));
         pl.attr = true;
     }
     // tile list: 128 rows of T1 against column segments of <= 256 rows of T2 (symmetric: from the row block's own
@@ -739,7 +843,7 @@ inline int i8_kgemm_run(I8Plan& pl, I8EncodeFn enc, cudaStream_t st, int nsm, co
         gp.ws = pl.ws;
         gp.counter = pl.d_counter;
         I8CK(cudaMemsetAsync(pl.d_counter, 0, sizeof(int), st));
-        i8_gemm_kernel<<<(unsigned)std::min<size_t>(nitems, (size_t)nsm), I8_THREADS, i8_smem_bytes(), st>>>(amap, bmap[0], bmap[1],
+        i8_pipeline_kernel<I8KgemmTraits><<<(unsigned)std::min<size_t>(nitems, (size_t)nsm), I8_THREADS, i8_smem_bytes(), st>>>(amap, bmap[0], bmap[1],
                                                                                                             bmap[2], gp);
         if (pl.prof[2] && passes == 0) cudaEventRecord(pl.prof[2], st);
         I8CrtParams cp;

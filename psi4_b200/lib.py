@@ -27,7 +27,7 @@ class Stats(ct.Structure):
         ("j_bytes", ct.c_double), ("half_flops", ct.c_double), ("half_bytes", ct.c_double),
         ("kgemm_flops", ct.c_double), ("launches", ct.c_uint64), ("hbm_tensor_bytes", ct.c_uint64),
         ("hbm_work_bytes", ct.c_uint64), ("n_shards", ct.c_int), ("q_begin", ct.c_int), ("q_end", ct.c_int),
-        ("reduce_kind", ct.c_int), ("kgemm_kind", ct.c_int), ("kgemm_moduli", ct.c_int),
+        ("reduce_kind", ct.c_int), ("kgemm_kind", ct.c_int), ("kgemm_moduli", ct.c_int), ("half_kind", ct.c_int),
     ]
 
     def as_dict(self):
@@ -62,6 +62,7 @@ SIGNATURES = {
     "b200jk_hbm_estimate": (ct.c_int, [ct.c_void_p, ct.c_size_t, ct.c_int, ct.POINTER(ct.c_uint64)]),
     "b200jk_set_work_budget": (ct.c_int, [ct.c_void_p, ct.c_uint64]),
     "b200jk_set_kgemm": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int]),
+    "b200jk_set_half": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int]),
     "b200jk_fill_synthetic": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_uint64, _dp]),
     "b200jk_download_rows": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_size_t, ct.c_size_t, ct.c_size_t, _dp]),
     "b200jk_dev_alloc": (ct.c_int, [ct.c_void_p, ct.c_size_t, ct.POINTER(ct.c_void_p)]),
@@ -331,6 +332,10 @@ class Engine:
 
     def set_work_budget(self, nbytes):
         self._check(self.L.b200jk_set_work_budget(self.h, nbytes))
+
+    def set_half(self, arm="auto", moduli=0):
+        """Arm of the half transform: "auto" | "dmma" | "i8" (INT8 tensor cores by residues, `moduli` 6..13, default 12)."""
+        self._check(self.L.b200jk_set_half(self.h, {"auto": 0, "dmma": 1, "i8": 2}[arm], int(moduli)))
 
     def set_kgemm(self, arm="auto", moduli=0):
         """Arm of the K GEMM: "auto" | "dmma" (FP64 tensor pipe) | "i8" (INT8 tensor cores by residues, `moduli` 6..13)."""

@@ -163,3 +163,105 @@ def test_i8_golden_vectors():
             assert np.abs(wK[i] - g[f"wK_{tag}{i}"]).max() < TOL
             assert np.abs(J[i] - g[f"J_{tag}{i}"]).max() < TOL
     e.close()
+
+
+# ---- the half transform on the INT8 tensor cores (psi4_b200/csrc/i8_half.cuh) -------------------------------------------
+
+
+@pytest.mark.parametrize("lr", [True, False])
+@pytest.mark.parametrize("density", [1.0, 0.4])
+@pytest.mark.parametrize("kgemm", ["dmma", "i8"])
+def test_i8_half_transform_matches_oracle(oracle, lr, density, kgemm):
+    """DFHelper::first_transform_pQq (lib3index/dfhelper.cc:2162-2186) by residues: screened and dense masks, ragged nocc
+    incl. 0 / 1 / odd, two different C matrices, with either arm of the K GEMM behind it.  The first J sweep rides on the
+    conversion of the tensor rows (I8HalfFuseJ)."""
+    rng = np.random.default_rng(21 + lr + int(10 * density))
+    n, a = 300, 150
+    keep = random_mask(rng, n, density)
+    sp, d, B, P = make(oracle, rng, n, a, keep, 0.1)
+    noccs = [23, 0, 1, 64]
+    Cl = [rng.standard_normal((n, o)) / np.sqrt(n) for o in noccs]
+    Cr = None if lr else [rng.standard_normal((n, o)) / np.sqrt(n) for o in noccs]
+    D = [x @ (x if lr else y).T for x, y in zip(Cl, Cl if lr else Cr)]
+    Jo, Ko, _, _ = oracle.build_JK(sp, P, Cl, Cr, D=D)
+    e = engine_for(d, P, n, a, kgemm)
+    e.set_half("i8")
+    J, K, _ = e.compute(Cl, Cr, D)
+    st = e.stats()
+    assert st["half_kind"] == 1, st
+    check(J, Jo, what="J")
+    check(K, Ko, what="K(half i8)")
+    assert not K[1].any()
+    J2, K2, _ = e.compute(Cl, Cr, D)
+    for x, y in zip(K, K2):
+        assert np.array_equal(x, y)  # run to run
+    e.set_half("dmma")
+    _, Kd, _ = e.compute(Cl, Cr, D)
+    assert e.stats()["half_kind"] == 0
+    check(K, Kd, tol=1e-11, what="half i8 vs half dmma")
+    e.close()
+
+
+def test_i8_half_wk_q_chunks_wide_nocc_and_tensor_change(oracle):
+    """wK (the other two tensors carry their own row scales), the K build in Q chunks, more than 256 occupied columns (two
+    orbital tiles), and a tensor that is uploaded again with other values (the row scales must follow it)."""
+    rng = np.random.default_rng(98)
+    n, a, o = 300, 260, 270
+    keep = banded_mask(n, 120)
+    sp, d, B, P = make(oracle, rng, n, a, keep, 0.05)
+    B1 = rng.standard_normal((a, n, n)) * 0.05
+    B1 = B1 + B1.transpose(0, 2, 1)
+    B2 = rng.standard_normal((a, n, n)) * 0.05
+    B2 = B2 + B2.transpose(0, 2, 1)
+    m1, w = d.pack(B1), d.pack(B2)
+    Cl = [np.linalg.qr(rng.standard_normal((n, o)))[0], np.linalg.qr(rng.standard_normal((n, 37)))[0]]
+    D = [c @ c.T for c in Cl]
+    Jo, Ko, wKo, _ = oracle.build_JK(sp, P, Cl, None, D=D, do_wK=True, m1Ppq=m1, wPpq=w)
+    e = engine_for(d, P, n, a, "i8", tensors={1: m1, 2: w})
+    e.set_half("i8")
+    J, K, wK = e.compute(Cl, None, D, do_wK=True)
+    assert e.stats()["half_kind"] == 1
+    check(J, Jo, what="J")
+    check(K, Ko, what="K")
+    check(wK, wKo, what="wK")
+    e.set_work_budget(2 * 128 * n * o * 8 + 1024)  # one 128-row chunk of T1 and T2 at a time
+    J, K, wK = e.compute(Cl, None, D, do_wK=True)
+    check(K, Ko, what="K chunked")
+    check(wK, wKo, what="wK chunked")
+    e.set_work_budget(0)
+    e.upload(0, 1024.0 * P)  # same handle, tensor 1024 times larger: K grows by 2^20 exactly if the scales were recomputed
+    _, K3, _ = e.compute(Cl, None, None, do_J=False)
+    for x, y in zip(K3, Ko):
+        assert np.abs(x / 1048576.0 - y).max() < TOL
+    e.close()
+
+
+def test_i8_half_golden_vectors():
+    """Both residue arms together against the vectors frozen from the reference's own object code."""
+    from psi4_b200 import DFHelper, Engine
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_jk_vectors.npz"))
+    keep = g["keep"]
+    n, a = keep.shape[0], int(g["naux"])
+    d = DFHelper(n, a)
+    d.prepare_sparsity(keep=keep)
+    e = Engine(1)
+    e.set_layout(n, a, d.small_skips_, d.big_skips_, d.schwarz_fun_index_)
+    e.upload(0, g["Ppq"])
+    e.upload(1, g["m1Ppq"])
+    e.upload(2, g["wPpq"])
+    e.set_kgemm("i8")
+    e.set_half("i8", 13)
+    nmat = len(g["noccs"])
+    for tag, lr in (("sym", True), ("gen", False)):
+        Cl = [g[f"Cl{i}"] for i in range(nmat)]
+        Cr = None if lr else [g[f"Cr{i}"] for i in range(nmat)]
+        D = [x @ (x if lr else y).T for x, y in zip(Cl, Cl if lr else Cr)]
+        J, K, wK = e.compute(Cl, Cr, D, do_wK=True)
+        st = e.stats()
+        assert st["kgemm_kind"] == 1 and st["half_kind"] == 1
+        for i in range(nmat):
+            assert np.abs(K[i] - g[f"K_{tag}{i}"]).max() < TOL
+            assert np.abs(wK[i] - g[f"wK_{tag}{i}"]).max() < TOL
+            assert np.abs(J[i] - g[f"J_{tag}{i}"]).max() < TOL
+    e.close()

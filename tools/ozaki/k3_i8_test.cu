@@ -1,0 +1,257 @@
+// Standalone check and timing of the INT8-tensor-core half transform (psi4_b200/csrc/i8_half.cuh) against a
+// double-double reference on sampled elements.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o k3_i8_test k3_i8_test.cu
+//   ./k3_i8_test nbf nq nocc density nmod arena_GB [reps]
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <string>
+#include <vector>
+
+#include "../../psi4_b200/csrc/i8_half.cuh"
+
+using namespace b2k;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e_)); exit(1); } } while (0)
+
+__host__ __device__ inline uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void fill_tensor(double* t, const size_t* row_off, const int* ldm, const int* sp, const int* cols, const size_t* cols_off,
+                            int nq, int nbf) {
+    const int m = blockIdx.y;
+    const int ld = ldm[m], K = sp[m];
+    const int* c = cols + cols_off[m];
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < (long)nq * ld; idx += (long)gridDim.x * blockDim.x) {
+        const int q = (int)(idx / ld), k = (int)(idx % ld);
+        double v = 0;
+        if (k < K) {
+            const int n = c[k];
+            const uint64_t h = mix64(((uint64_t)q << 40) ^ ((uint64_t)min(m, n) << 20) ^ (uint64_t)max(m, n));
+            const double u = (double)(h >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+            v = u * ldexp(1.0, -(int)((h >> 2) & 15)) * ldexp(1.0, (q % 7) - 3);
+        }
+        t[row_off[m] + (size_t)q * ld + k] = v;
+    }
+}
+__device__ __forceinline__ void two_sum(double a, double b, double& s, double& e) {
+    s = a + b;
+    const double bb = s - a;
+    e = (a - (s - bb)) + (b - bb);
+}
+// one block per sample (m, q, i)
+__global__ void ref_kernel(const double* t, const size_t* row_off, const int* ldm, const int* sp, const int* cols, const size_t* cols_off,
+                           const double* Ct, int ldc, const int3* samples, double* out, double* scale) {
+    const int3 s = samples[blockIdx.x];
+    const int m = s.x, q = s.y, i = s.z;
+    const double* b = t + row_off[m] + (size_t)q * ldm[m];
+    const int* c = cols + cols_off[m];
+    double hi = 0, lo = 0, nb = 0, nc = 0;
+    for (int k = threadIdx.x; k < sp[m]; k += blockDim.x) {
+        const double x = b[k], y = Ct[(size_t)i * ldc + c[k]];
+        const double p = x * y, pe = fma(x, y, -p);
+        double ss, e;
+        two_sum(hi, p, ss, e);
+        hi = ss;
+        lo += e + pe;
+        nb = fma(x, x, nb);
+        nc = fma(y, y, nc);
+    }
+    __shared__ double sh[128], sl[128], sa[128], sb[128];
+    sh[threadIdx.x] = hi;
+    sl[threadIdx.x] = lo;
+    sa[threadIdx.x] = nb;
+    sb[threadIdx.x] = nc;
+    __syncthreads();
+    for (int w = 64; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) {
+            double ss, e;
+            two_sum(sh[threadIdx.x], sh[threadIdx.x + w], ss, e);
+            sh[threadIdx.x] = ss;
+            sl[threadIdx.x] += sl[threadIdx.x + w] + e;
+            sa[threadIdx.x] += sa[threadIdx.x + w];
+            sb[threadIdx.x] += sb[threadIdx.x + w];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[blockIdx.x] = sh[0] + sl[0];
+        scale[blockIdx.x] = sqrt(sa[0] * sb[0]);
+    }
+}
+
+int main(int argc, char** argv) {
+    const int nbf = argc > 1 ? atoi(argv[1]) : 300;
+    const int nq = argc > 2 ? atoi(argv[2]) : 500;
+    const int o = argc > 3 ? atoi(argv[3]) : 37;
+    const double density = argc > 4 ? atof(argv[4]) : 0.7;
+    const int nmod = argc > 5 ? atoi(argv[5]) : 12;
+    const double arena_gb = argc > 6 ? atof(argv[6]) : 1.0;
+    const int reps = argc > 7 ? atoi(argv[7]) : 2;
+    const int cluster = argc > 8 ? atoi(argv[8]) : 1;
+    const int op = (o + 1) & ~1;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    const int nsm = prop.multiProcessorCount;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+    I8EncodeFn enc = (I8EncodeFn)fn;
+
+    // mask: banded + random, symmetric, diagonal kept
+    std::vector<int> sp(nbf), ldm(nbf), cols;
+    std::vector<size_t> cols_off(nbf), row_off(nbf);
+    size_t unit = 0;
+    for (int m = 0; m < nbf; m++) {
+        cols_off[m] = cols.size();
+        for (int n = 0; n < nbf; n++) {
+            const uint64_t h = mix64(((uint64_t)std::min(m, n) << 32) | (uint64_t)std::max(m, n));
+            const bool keep = m == n || (double)(h >> 11) * (1.0 / 9007199254740992.0) < density;
+            if (keep) cols.push_back(n);
+        }
+        sp[m] = (int)(cols.size() - cols_off[m]);
+        ldm[m] = (sp[m] + 3) / 4 * 4;
+        row_off[m] = unit * (size_t)nq;
+        unit += ldm[m];
+    }
+    const size_t tdoubles = unit * (size_t)nq;
+    printf("K3-i8 test: nbf=%d nq=%d nocc=%d kept pairs=%zu (%.1f %%) tensor %.2f GB\n", nbf, nq, o, cols.size(),
+           100.0 * cols.size() / ((double)nbf * nbf), tdoubles * 8e-9);
+    double *tensor, *Ct, *T;
+    int *d_sp, *d_ldm, *d_cols;
+    size_t *d_cols_off, *d_row_off;
+    CK(cudaMalloc(&tensor, tdoubles * 8));
+    CK(cudaMalloc(&d_sp, nbf * 4));
+    CK(cudaMalloc(&d_ldm, nbf * 4));
+    CK(cudaMalloc(&d_cols, cols.size() * 4));
+    CK(cudaMalloc(&d_cols_off, nbf * 8));
+    CK(cudaMalloc(&d_row_off, nbf * 8));
+    CK(cudaMemcpy(d_sp, sp.data(), nbf * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_ldm, ldm.data(), nbf * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_cols, cols.data(), cols.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_cols_off, cols_off.data(), nbf * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_row_off, row_off.data(), nbf * 8, cudaMemcpyHostToDevice));
+    fill_tensor<<<dim3(64, nbf), 256>>>(tensor, d_row_off, d_ldm, d_sp, d_cols, d_cols_off, nq, nbf);
+    const int ldc = (nbf + 3) / 4 * 4;
+    std::vector<double> hCt((size_t)op * ldc, 0.0);
+    for (int i = 0; i < o; i++)
+        for (int n = 0; n < nbf; n++) {
+            const uint64_t h = mix64(0xC0FFEEull + (uint64_t)i * 100003ull + n);
+            hCt[(size_t)i * ldc + n] = ((double)(h >> 11) * (1.0 / 9007199254740992.0) - 0.5) * 2.0 / sqrt((double)nbf) * (1 + (i % 5));
+        }
+    CK(cudaMalloc(&Ct, hCt.size() * 8));
+    CK(cudaMemcpy(Ct, hCt.data(), hCt.size() * 8, cudaMemcpyHostToDevice));
+    const size_t Tpitch = (size_t)nq * op;
+    CK(cudaMalloc(&T, (size_t)nbf * Tpitch * 8));
+    CK(cudaMemset(T, 0xFF, (size_t)nbf * Tpitch * 8));
+    CK(cudaDeviceSynchronize());
+
+    I8HalfPlan pl;
+    std::string err;
+    if (i8h_set_layout(pl, sp, &err)) {
+        printf("set_layout: %s\n", err.c_str());
+        return 1;
+    }
+    size_t mn, all;
+    i8h_arena_need(pl, nmod, nq, o, cluster, &mn, &all);
+    pl.arena_cap = std::min(all, (size_t)(arena_gb * 1e9));
+    if (pl.arena_cap < mn) pl.arena_cap = mn;
+    CK(cudaMalloc((void**)&pl.arena, pl.arena_cap));
+    for (int i = 0; i < 5; i++) CK(cudaEventCreate(&pl.prof[i]));
+    {  // constants of i8_kgemm.cuh
+        I8Consts c;
+        i8_fill_consts(c);
+        CK(cudaMemcpyToSymbol(c_i8, &c, sizeof c));
+    }
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    I8HalfInfo info;
+    float best = 1e30f, bp[4] = {1e30f, 1e30f, 1e30f, 1e30f};
+    for (int r = 0; r < reps + 1; r++) {
+        CK(cudaEventRecord(e0, 0));
+        int rc = i8_half_run(pl, 0, nsm, tensor, 0, d_row_off, d_ldm, d_sp, d_cols, d_cols_off, nbf, nq, Ct, ldc, o, op, o, 0, nq, T,
+                             Tpitch, nmod, cluster, nullptr, &info, &err);
+        CK(cudaEventRecord(e1, 0));
+        if (rc) {
+            printf("i8_half_run rc=%d: %s\n", rc, err.c_str());
+            return 1;
+        }
+        CK(cudaDeviceSynchronize());
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (r > 0 && ms < best) best = ms;  // the first call also computes the row scales of the tensor
+        for (int i = 0; i < 4; i++) {
+            float t;
+            CK(cudaEventElapsedTime(&t, pl.prof[i], pl.prof[i + 1]));
+            if (t < bp[i]) bp[i] = t;
+        }
+    }
+    const double flops = 2.0 * nq * (double)cols.size() * o;
+    printf("  cluster=%d nmod=%d bits=%.2f chunks=%d ntile_n=%d arena %.2f GB (all-in-one %.2f GB)\n", cluster, info.nmod, info.bits, info.nchunks, info.ntile_n,
+           pl.arena_cap * 1e-9, all * 1e-9);
+    printf("  total %.3f ms -> %.1f TFLOP/s FP64-equivalent; chunk 0: convert %.3f gather %.3f gemm %.3f crt %.3f ms\n", best,
+           flops / best * 1e-9, bp[0], bp[1], bp[2], bp[3]);
+
+    // reference on samples
+    const int ns = 8192;
+    std::vector<int3> samples(ns);
+    uint64_t s = 4242;
+    for (int i = 0; i < ns; i++) {
+        s = mix64(s);
+        int m = (int)(s % nbf);
+        s = mix64(s);
+        int q = (int)(s % nq);
+        s = mix64(s);
+        int ii = (int)(s % o);
+        if (i < 64) q = nq - 1 - (i & 3);
+        if (i >= 64 && i < 128) m = nbf - 1 - (i & 3);
+        if (i >= 128 && i < 192) ii = o - 1;
+        samples[i] = make_int3(m, q, ii);
+    }
+    int3* dsm;
+    double *dref, *dscale;
+    CK(cudaMalloc(&dsm, ns * sizeof(int3)));
+    CK(cudaMalloc(&dref, ns * 8));
+    CK(cudaMalloc(&dscale, ns * 8));
+    CK(cudaMemcpy(dsm, samples.data(), ns * sizeof(int3), cudaMemcpyHostToDevice));
+    ref_kernel<<<ns, 128>>>(tensor, d_row_off, d_ldm, d_sp, d_cols, d_cols_off, Ct, ldc, dsm, dref, dscale);
+    CK(cudaDeviceSynchronize());
+    std::vector<double> ref(ns), sc(ns), got(ns);
+    CK(cudaMemcpy(ref.data(), dref, ns * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(sc.data(), dscale, ns * 8, cudaMemcpyDeviceToHost));
+    double max_abs = 0, max_rel = 0, max_t = 0;
+    int worst = 0;
+    for (int i = 0; i < ns; i++) {
+        double g;
+        CK(cudaMemcpy(&g, T + (size_t)samples[i].x * Tpitch + (size_t)samples[i].y * op + samples[i].z, 8, cudaMemcpyDeviceToHost));
+        const double d = fabs(g - ref[i]);
+        if (!(d <= max_abs)) {
+            max_abs = d;
+            worst = i;
+        }
+        if (sc[i] > 0 && !(d / sc[i] <= max_rel)) max_rel = d / sc[i];
+        max_t = fmax(max_t, fabs(ref[i]));
+    }
+    // pad columns must be zero
+    double padmax = 0;
+    if (op > o) {
+        for (int i = 0; i < 64; i++) {
+            double g;
+            CK(cudaMemcpy(&g, T + (size_t)samples[i].x * Tpitch + (size_t)samples[i].y * op + o, 8, cudaMemcpyDeviceToHost));
+            padmax = fmax(padmax, fabs(g));
+        }
+    }
+    printf("  vs double-double on %d samples: max|dT| = %.3e (sample %d: m=%d q=%d i=%d), max|dT|/(|b||c|) = %.3e = 2^%.1f, max|T| = %.3e, pad %.1e\n",
+           ns, max_abs, worst, samples[worst].x, samples[worst].y, samples[worst].z, max_rel, max_rel > 0 ? log2(max_rel) : -999.0, max_t, padmax);
+    const bool ok = max_rel < ldexp(1.0, -(int)info.bits + 3) && padmax == 0;
+    printf("%s\n", ok ? "OK" : "FAILED");
+    return ok ? 0 : 2;
+}
