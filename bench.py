@@ -54,6 +54,10 @@ def parse():
     ap.add_argument("--no-extra", action="store_true", help="headline workload only (no `workloads` block, no cuBLAS calibration)")
     ap.add_argument("--no-spot", action="store_true", help="skip the host-side spot parity (ncu / profiling runs)")
     ap.add_argument("--skip-probes", action="store_true", help="no FP64 ceiling probes (ncu launch lists); roofline.peak = last recorded")
+    ap.add_argument("--kgemm", default="auto", choices=["auto", "dmma", "i8"],
+                    help="arm of the K GEMM: FP64 tensor pipe (dmma) or INT8 tensor cores by residues (i8); auto = the engine's rule")
+    ap.add_argument("--half", default="auto", choices=["auto", "dmma", "i8"], help="the same for the half transform")
+    ap.add_argument("--no-ab", action="store_true", help="skip the extra timed builds with both arms on the FP64 tensor pipe")
     ap.add_argument("--nonsymmetric", action="store_true", help="C_right != C_left (general path)")
     ap.add_argument("--response", type=int, default=0, metavar="R",
                     help="R right-hand sides sharing ONE C_left with R different C_right, the shape of the reference's "
@@ -325,6 +329,8 @@ def measure(args, ds, name, steps, warmup, headline):
     t0 = time.perf_counter()
     eng = Engine(rank=rank, world=world, device=ds.local_rank, nccl_id=ds.nccl_id(Engine))
     eng.set_layout(nbf, naux, d.small_skips_, d.big_skips_, d.schwarz_fun_index_)
+    eng.set_kgemm(args.kgemm)
+    eng.set_half(args.half)
     layout_s = time.perf_counter() - t0
     t0 = time.perf_counter()
     eng.fill_synthetic(0, workloads.SEED, amp)
@@ -440,6 +446,28 @@ def measure(args, ds, name, steps, warmup, headline):
                      "wall_s": time.perf_counter() - t0, "eigenvalues_kept": int(kept)}
         except Exception as ex:  # never let the extra cost the bench line
             setup = {"error": str(ex)[:200]}
+    # ---- A/B: the same build with both GEMMs on the FP64 tensor pipe (DMMA), device-resident operands, outside the timed
+    # region of the headline: the north_star's "DMMA utilisation against FP64 peak" stays measured when an INT8 arm is the default
+    fp64_arms = None
+    if headline and not args.no_ab and (st_dev["kgemm_kind"] or st_dev["half_kind"]):
+        eng.set_kgemm("dmma")
+        eng.set_half("dmma")
+        eng.compute_device(dC, dCr, noccs, dD, dJ, dK, None)
+        ab = {"ms_total": 0.0, "ms_j": 0.0, "ms_half": 0.0, "ms_kgemm": 0.0}
+        nab = 3
+        for _ in range(nab):
+            eng.compute_device(dC, dCr, noccs, dD, dJ, dK, None)
+            st = eng.stats()
+            for k in ab:
+                ab[k] += st[k] / nab
+        for k in ab:
+            ab[k] = ds.max(ab[k])
+        ab["max_abs_dK_vs_default_arms"] = None
+        if fetch:
+            ab["max_abs_dK_vs_default_arms"] = float(max(np.abs(eng.dev_get(dK[i], (nbf, nbf)) - K[i]).max() for i in range(nmat)))
+        fp64_arms = ab
+        eng.set_kgemm(args.kgemm)
+        eng.set_half(args.half)
     ds.barrier()
     reduce_kind = {0: "none (one GPU)", 1: "fixed-rank-order peer-memory kernel over NVLink (peer_reduce.cuh)",
                    2: "NCCL all-reduce"}.get(st_dev["reduce_kind"], "?")
@@ -447,7 +475,7 @@ def measure(args, ds, name, steps, warmup, headline):
     res = dict(cfg=cfg, keep=keep, amp=amp, Cl=Cl, Crl=Crl, value=value, wall_ms=wall_ms, parts=parts, st_dev=st_dev,
                e2e_ms=e2e_ms, e2e_parts=e2e_parts, launches=launches, clk=clk, arms_equal=bool(arms_equal), arms_diff=arms_diff,
                run_equal=bool(run_equal), ranks_equal=bool(ranks_equal), spot=spot, pk_dmma=pk_dmma, pk_dfma=pk_dfma,
-               layout_s=layout_s, fill_s=fill_s, reduce_kind=reduce_kind, setup=setup,
+               layout_s=layout_s, fill_s=fill_s, reduce_kind=reduce_kind, setup=setup, fp64_arms=fp64_arms,
                h2d=int(nmat * (Cl[0].nbytes * (1 if Crl is None else 2) + n2b)), d2h=int(nmat * 2 * n2b))
     return res
 
@@ -457,11 +485,13 @@ def kernel_table(res, peak_dmma, hbm_peak, peak_src):
     half_tf = st["half_flops"] / (parts["ms_half"] * 1e-3) / 1e12 if parts["ms_half"] else 0.0
     kg_tf = st["kgemm_flops"] / (parts["ms_kgemm"] * 1e-3) / 1e12 if parts["ms_kgemm"] else 0.0
     j_gbs = st["j_bytes"] / (parts["ms_j"] * 1e-3) / 1e9 if parts["ms_j"] else 0.0
+    arm = {0: "FP64 tensor pipe (DMMA m8n8k4)", 1: "INT8 tensor cores (tcgen05.mma.kind::i8) by residues + CRT; tflops = FP64-equivalent"}
     return {
-        "half_transform": {"ms": parts["ms_half"], "tflops": half_tf,
+        "half_transform": {"ms": parts["ms_half"], "tflops": half_tf, "arm": arm[st.get("half_kind", 0)],
                            "frac_of_dmma_peak": half_tf / peak_dmma if peak_dmma else None,
                            "hbm_read_gbs": st["half_bytes"] / (parts["ms_half"] * 1e-3) / 1e9 if parts["ms_half"] else 0.0},
-        "k_gemm": {"ms": parts["ms_kgemm"], "tflops": kg_tf, "frac_of_dmma_peak": kg_tf / peak_dmma if peak_dmma else None},
+        "k_gemm": {"ms": parts["ms_kgemm"], "tflops": kg_tf, "arm": arm[st.get("kgemm_kind", 0)],
+                   "moduli": st.get("kgemm_moduli", 0), "frac_of_dmma_peak": kg_tf / peak_dmma if peak_dmma else None},
         "j_sweeps": {"ms": parts["ms_j"], "gbs": j_gbs, "frac_of_hbm_peak": j_gbs / hbm_peak, "hbm_peak_gbs": hbm_peak,
                      "hbm_peak_source": peak_src},
         "cross_gpu_sum": {"ms": parts["ms_allreduce"], "how": res["reduce_kind"]},
@@ -581,6 +611,17 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get("half_transform")
     except Exception:
         pass
+    ab = res["fp64_arms"]
+    if ab and res["st_dev"]["half_kind"]:
+        # the headline ran the half transform on the INT8 tensor cores: the FP64 roofline of K3 is that of the A/B builds
+        half_tf = res["st_dev"]["half_flops"] / (ab["ms_half"] * 1e-3) / 1e12 if ab["ms_half"] else 0.0
+    if ab:
+        st0 = res["st_dev"]
+        ab["half_transform_tflops"] = st0["half_flops"] / (ab["ms_half"] * 1e-3) / 1e12 if ab["ms_half"] else 0.0
+        ab["k_gemm_tflops"] = st0["kgemm_flops"] / (ab["ms_kgemm"] * 1e-3) / 1e12 if ab["ms_kgemm"] else 0.0
+        ab["half_transform_frac_of_dmma_peak"] = ab["half_transform_tflops"] / peak_dmma if peak_dmma else None
+        ab["k_gemm_frac_of_dmma_peak"] = ab["k_gemm_tflops"] / peak_dmma if peak_dmma else None
+        ab["what"] = "the same build with both GEMMs on the FP64 tensor pipe (B200JK_KGEMM=dmma B200JK_HALF=dmma), 3 device-resident builds"
     roofline = {"kernel": "half_ws_kernel (K3)", "bound": "tensor", "achieved": half_tf, "peak": peak_dmma,
                 "unit": "TFLOP/s", "frac": half_tf / peak_dmma if peak_dmma else None, "traffic": traffic,
                 "traffic_source": "profiles/traffic.json (ncu --set full capture of this kernel, recorded, not re-measured in this run)",
@@ -624,7 +665,7 @@ def main():
         "parity_spot": res["spot"], "workloads": wl,
         "hbm": {"tensor_gb": res["st_dev"]["hbm_tensor_bytes"] / 1e9, "work_gb": res["st_dev"]["hbm_work_bytes"] / 1e9,
                 "fill_s": res["fill_s"], "layout_s": res["layout_s"]},
-        "setup": res["setup"],
+        "setup": res["setup"], "fp64_arms": res["fp64_arms"],
     }
     emit(line)
     ds.close()

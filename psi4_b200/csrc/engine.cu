@@ -1052,7 +1052,9 @@ int run_device_K(b200jk* h, Shard& s, const Task& t, const double* const* dCl, c
             double* Kout = (wk ? outW : outK) + i * n2;
             FuseJ fj_store, *fj = nullptr;
             // the density row can ride on either transform of the Ppq tensor: on T1 normally, on T2 when T1 is reused
-            if (!wk && t.do_J && dD && dD[i] && can_fuse_j(o)) {
+            // (INT8 arm with the planes of the whole shard still resident: the conversion the sweep would ride on is skipped)
+            const bool planes_cached = half_want_i8(h, s, o) && qc >= s.nq && i8h_cached(s.i8h, tenL, 0, s.nq, half_moduli(h));
+            if (!wk && t.do_J && dD && dD[i] && can_fuse_j(o) && !planes_cached) {
                 const int ldd = round_up((int)N, 2);
                 fj_store.Dm = s.Dm + (size_t)i * N * ldd;
                 fj_store.ldd = ldd;

@@ -158,6 +158,10 @@ __global__ void __launch_bounds__(128) i8h_gather_kernel(const int8_t* __restric
         int n[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) n[e] = (k + e < K) ? __ldg(c + k + e) : -1;
+        // kept partners come in runs: four consecutive columns are one unaligned 32-bit window of the rc row (two aligned
+        // loads and a funnel shift instead of four byte loads)
+        const bool run = n[0] >= 0 && n[1] == n[0] + 1 && n[2] == n[0] + 2 && n[3] == n[0] + 3;
+        const int nw = n[0] & ~3, sh = (n[0] & 3) * 8;
         const int kb = k >> 7, kk = k & 127;
 #pragma unroll
         for (int di = 0; di < 4; di++) {
@@ -169,9 +173,15 @@ __global__ void __launch_bounds__(128) i8h_gather_kernel(const int8_t* __restric
                 uint32_t w = 0;
                 if (i < o) {
                     const int8_t* src = rc + (size_t)j * rc_plane + (size_t)i * rc_ld;
+                    if (run) {
+                        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(src + nw);
+                        const uint32_t w1 = sh ? *reinterpret_cast<const uint32_t*>(src + nw + 4) : 0u;
+                        w = __funnelshift_r(w0, w1, sh);
+                    } else {
 #pragma unroll
-                    for (int e = 0; e < 4; e++)
-                        if (n[e] >= 0) w |= ((uint32_t)(uint8_t)src[n[e]]) << (8 * e);
+                        for (int e = 0; e < 4; e++)
+                            if (n[e] >= 0) w |= ((uint32_t)(uint8_t)src[n[e]]) << (8 * e);
+                    }
                 }
                 *reinterpret_cast<uint32_t*>(d + (size_t)j * cg_plane) = w;
             }
@@ -459,11 +469,16 @@ struct I8HalfPlan {  // per shard
     uint64_t launches = 0;
     bool consts = false;
     int crt_nmod = 0;  // moduli the constants of the floating-point CRT were uploaded for
+    // When the arena holds the planes of the whole Q range in one chunk they stay valid until the tensor changes: the next
+    // build (and the second density of an open-shell build) skips the conversion -- which is most of the arm's time.
+    int cache_which = -1, cache_qbeg = -1, cache_qc = -1, cache_nmod = -1;
+    uint64_t conversions_skipped = 0;
     cudaEvent_t prof[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // optional: start / convert / gather / GEMM / CRT of chunk 0
     void release_arena() {
         if (arena) cudaFree(arena);
         arena = nullptr;
         arena_cap = 0;
+        cache_which = -1;
     }
     void release() {
         release_arena();
@@ -493,8 +508,19 @@ inline int i8h_set_layout(I8HalfPlan& pl, const std::vector<int>& sp, std::strin
     pl.d_kboff = nullptr;
     I8CK(cudaMalloc((void**)&pl.d_kboff, (nbf + 1) * sizeof(int)));
     I8CK(cudaMemcpy(pl.d_kboff, pl.kboff.data(), (nbf + 1) * sizeof(int), cudaMemcpyHostToDevice));
-    for (int i = 0; i < 3; i++) pl.expo_valid[i] = false;
+    for (int i = 0; i < 3; i++) {  // a new layout: the row scales (sized nbf x nq of the old one) and the cached planes go
+        if (pl.expoB[i]) cudaFree(pl.expoB[i]);
+        pl.expoB[i] = nullptr;
+        pl.expo_valid[i] = false;
+    }
+    pl.cache_which = -1;
     return 0;
+}
+
+// true if the planes of (tensor which, Q range, moduli) are still in the arena from an earlier call
+inline bool i8h_cached(const I8HalfPlan& pl, int which, int qbeg, int qc, int nmod) {
+    return pl.arena && pl.cache_which == which && pl.cache_qbeg == qbeg && pl.cache_qc == qc && pl.cache_nmod == nmod &&
+           pl.expo_valid[which] && pl.expo_nmod[which] == nmod;
 }
 
 template <int NMOD>
@@ -561,7 +587,7 @@ inline int i8h_launch_gemm(const I8HalfParams& gp, int nsm, cudaStream_t st, std
 }
 
 struct I8HalfInfo {
-    int nmod = 0, nchunks = 0, ntile_n = 0, nit = 0, cluster = 0;
+    int nmod = 0, nchunks = 0, ntile_n = 0, nit = 0, cluster = 0, cached = 0;
     double bits = 0;
     size_t arena = 0;
 };
@@ -688,19 +714,27 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
         if (err) *err = "scratch arena accounting";
         return 3;
     }
+    const bool cached = chunks.size() == 1 && i8h_cached(pl, which, qbeg, qc, nmod);
+    if (cached && fuse) {
+        if (err) *err = "the first J sweep cannot ride on a conversion that is skipped (planes cached)";
+        return 2;
+    }
+    if (!cached) pl.cache_which = -1;
     int nch = 0;
     for (auto& c : chunks) {
         const int nmc = c.m1 - c.m0;
         const bool prof = pl.prof[0] && nch == 0;
         if (prof) cudaEventRecord(pl.prof[0], st);
+        if (cached) pl.conversions_skipped++;
         I8HalfFuseJ fjv = {nullptr, 0, nullptr, 0, nullptr, nullptr};
         if (fuse) {
             fjv = *fuse;
             fjv.cols = d_cols;
             fjv.cols_off = d_cols_off;
         }
-        I8H_DISPATCH(nmod, i8h_launch_convert, tensor, d_row_off, d_ldm, d_sp, pl.d_kboff, pl.expoB[which], nq, c.m0, nmc, qbeg, qc, nqt, planes,
-                     plane_stride, fjv, st);
+        if (!cached)
+            I8H_DISPATCH(nmod, i8h_launch_convert, tensor, d_row_off, d_ldm, d_sp, pl.d_kboff, pl.expoB[which], nq, c.m0, nmc, qbeg, qc, nqt,
+                         planes, plane_stride, fjv, st);
         if (prof) cudaEventRecord(pl.prof[1], st);
         i8h_gather_kernel<<<dim3((unsigned)nmc, (unsigned)((opw + 3) / 4)), 128, 0, st>>>(pl.rc, rc_ld, rc_plane, o, nmod, d_sp, pl.d_kboff, d_cols,
                                                                                         d_cols_off, c.m0, nit, ntile_n, cg, cg_plane);
@@ -749,7 +783,14 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
         I8CK(cudaGetLastError());
         nch++;
     }
+    if (chunks.size() == 1) {
+        pl.cache_which = which;
+        pl.cache_qbeg = qbeg;
+        pl.cache_qc = qc;
+        pl.cache_nmod = nmod;
+    }
     if (info) {
+        info->cached = cached ? 1 : 0;
         info->nmod = nmod;
         info->nchunks = nch;
         info->ntile_n = ntile_n;

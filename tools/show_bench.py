@@ -29,3 +29,6 @@ for f in sys.argv[1:]:
         kern(v["kernels"], "      ")
     cb = d.get("cpu_baseline")
     print("   cpu", cb and round(cb["value"], 1), cb and cb["cores"], " clocks", d.get("clocks"))
+    ab = d.get("fp64_arms")
+    if ab:
+        print("   fp64 arms:", {a: (round(b, 3) if isinstance(b, float) else b) for a, b in ab.items() if a != "what"})
