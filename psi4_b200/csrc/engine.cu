@@ -258,12 +258,37 @@ int fail(b200jk* h, int code, const char* fmt, ...) {
             return fail(h, B200JK_ERR_NCCL, "%s: %s (%s:%d)", #call, g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
     } while (0)
 
+// cudaMalloc that gives the engine's own elastic scratch back first: the residue arenas of the INT8 arms take what is
+// free when they are sized, and a later request (T2 of a non-symmetric build, a second tensor, gradient buffers) must
+// not fail because of them.  They are rebuilt (smaller) by the next build that wants them.
+cudaError_t malloc_elastic(b200jk* h, void** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaErrorMemoryAllocation || !h) return e;
+    cudaGetLastError();
+    int dev = -1;
+    cudaGetDevice(&dev);
+    bool freed = false;
+    for (auto& s : h->sh) {
+        if (s.dev != dev) continue;
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        if (s.i8h.arena) {
+            s.i8h.release_arena();
+            freed = true;
+        }
+        if (s.i8.planes[0] || s.i8.planes[1] || s.i8.ws) {
+            s.i8.release();
+            freed = true;
+        }
+    }
+    return freed ? cudaMalloc(p, bytes) : e;
+}
+
 template <class T>
 int upload_vec(b200jk* h, T** dptr, const std::vector<T>& v) {
     if (*dptr) cudaFree(*dptr);
     *dptr = nullptr;
     size_t n = std::max<size_t>(v.size(), 1);
-    CK(cudaMalloc((void**)dptr, n * sizeof(T)));
+    CK(malloc_elastic(h, (void**)dptr, n * sizeof(T)));
     if (!v.empty()) CK(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     return 0;
 }
@@ -273,7 +298,7 @@ int grow(b200jk* h, double** p, size_t* cap, size_t need) {
     if (*p) CK(cudaFree(*p));
     *p = nullptr;
     *cap = 0;
-    CK(cudaMalloc((void**)p, need * sizeof(double)));
+    CK(malloc_elastic(h, (void**)p, need * sizeof(double)));
     *cap = need;
     return 0;
 }
@@ -610,7 +635,9 @@ int half_want_i8(const b200jk* h, const Shard& s, int o) {
     const int arm = h->half_arm ? h->half_arm : env;
     if (arm == 1 || use_legacy() || o <= 0) return 0;
     if (arm == 2) return 1;
-    return 0;  // automatic: the DMMA arm
+    // automatic: from 256 basis functions, 16 occupied orbitals and 2^27 tensor elements per shard on (smaller builds
+    // are launch-bound and stay on the single DMMA kernel)
+    return h->nbf >= 256 && o >= 16 && (double)s.nq * (double)h->small_skips[h->nbf] >= 134217728.0;
 }
 int half_moduli(const b200jk* h) {
     static int env = -1;
@@ -622,16 +649,20 @@ int half_moduli(const b200jk* h) {
     return std::max(I8_MINMOD, std::min(I8_MAXMOD, n));
 }
 
-// K3 on the INT8 tensor cores (i8_half.cuh).  Returns -1 when no scratch arena can be had (the caller then takes the
-// DMMA arm).  max_o: the largest nocc of the build.
-int run_half_i8(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o, int op, int max_o, int qbeg, int qc, double* T,
-                const FuseJ* fj) {
+// Size the scratch arena of the INT8 half transform for this build (largest nocc, Q chunk).  Returns -1 when not even one
+// row-block fits beside everything else; *cacheable: the planes of the whole chunk fit at once, so they stay valid across
+// builds (i8h_cached) -- and the first J sweep must then NOT ride on the conversion, or the first build (conversion runs)
+// and the later ones (skipped) would sum d_Q in different orders.
+int half_i8_cluster() {
     static int cl_env = -1;
     if (cl_env < 0) {
         const char* e = getenv("B200JK_I8_CLUSTER");
-        cl_env = e ? atoi(e) : 2;
+        cl_env = e ? atoi(e) : 1;
     }
-    const int nmod = half_moduli(h), cluster = cl_env;
+    return cl_env;
+}
+int half_i8_arena(b200jk* h, Shard& s, int max_o, int qc, int op, bool two_operands, bool* cacheable) {
+    const int nmod = half_moduli(h), cluster = half_i8_cluster();
     const int nbf = (int)h->nbf;
     size_t mn = 0, all = 0;
     i8h_arena_need(s.i8h, nmod, qc, max_o, cluster, &mn, &all);
@@ -641,9 +672,9 @@ int run_half_i8(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o
         CK(cudaMemGetInfo(&free_b, &total_b));
         size_t avail = free_b + s.i8h.arena_cap;
         size_t k4 = 0;
-        if (kgemm_want_i8(h, qc * op) && !s.i8.planes_cap[0])
-            k4 = (size_t)kgemm_moduli(h) * nbf * ((size_t)qc * op + 128) * 2 + ((size_t)3 << 30);
-        const size_t reserve = (size_t)2 << 30;
+        if (kgemm_want_i8(h, qc * op) && !s.i8.planes_cap[0])  // planes of one operand (two when C_right differs) + residues
+            k4 = (size_t)kgemm_moduli(h) * nbf * ((size_t)qc * op + 128) * (two_operands ? 2 : 1) + ((size_t)4 << 30);
+        const size_t reserve = (size_t)4 << 30;
         if (avail < k4 + reserve + mn) return -1;
         const size_t want = std::min(all, avail - k4 - reserve);
         if (want > s.i8h.arena_cap) {
@@ -656,6 +687,17 @@ int run_half_i8(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o
             s.i8h.arena_cap = want;
         }
     }
+    if (cacheable) *cacheable = s.i8h.arena_cap >= all;
+    return 0;
+}
+
+// K3 on the INT8 tensor cores (i8_half.cuh).  Returns -1 when no scratch arena can be had (the caller then takes the
+// DMMA arm).  max_o: the largest nocc of the build.
+int run_half_i8(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o, int op, int max_o, int qbeg, int qc, double* T,
+                const FuseJ* fj, bool two_operands) {
+    const int nmod = half_moduli(h), cluster = half_i8_cluster();
+    const int nbf = (int)h->nbf;
+    if (half_i8_arena(h, s, max_o, qc, op, two_operands, nullptr) < 0) return -1;
     std::string err;
     I8HalfInfo info;
     I8HalfFuseJ f8 = {nullptr, 0, nullptr, 0, nullptr, nullptr};
@@ -677,9 +719,9 @@ int run_half_i8(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o
 
 // T[m][q][i] for q in the chunk [qbeg, qbeg+qc): one launch over (i-tiles, q-tiles, m).
 int run_half(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o, int op, int qbeg, int qc, double* T,
-             const FuseJ* fj = nullptr, int max_o = 0) {
+             const FuseJ* fj = nullptr, int max_o = 0, bool two_operands = false) {
     if (half_want_i8(h, s, o)) {
-        int rc = run_half_i8(h, s, which, Ct, ldc, o, op, std::max(max_o, o), qbeg, qc, T, fj);
+        int rc = run_half_i8(h, s, which, Ct, ldc, o, op, std::max(max_o, o), qbeg, qc, T, fj, two_operands);
         if (rc >= 0) return rc;
     }
     s.half_kind = 0;
@@ -751,16 +793,23 @@ int run_kgemm_i8(b200jk* h, Shard& s, const double* T1, const double* T2, int kd
     const int nmod = kgemm_moduli(h);
     const int klen = klen_env > 0 ? klen_env : 8192;
     const int nbf = (int)h->nbf, nop = symmetric ? 1 : 2;
-    size_t free_b = 0, total_b = 0;
-    CK(cudaMemGetInfo(&free_b, &total_b));
-    const size_t held = s.i8.planes_cap[0] + s.i8.planes_cap[1] + s.i8.ws_cap;
     const size_t ntile_est = (size_t)((nbf + I8_TM - 1) / I8_TM) * ((nbf + I8_TN - 1) / I8_TN + 1);
     const size_t ws_est = ((size_t)(kdim + klen - 1) / klen) * nmod * ntile_est * I8_TILE_BYTES;
-    const size_t reserve = (size_t)1 << 30;
-    const size_t avail = free_b + held;
-    const size_t min_planes = (size_t)nmod * nbf * nop * (size_t)std::min(kdim, 4 * klen);
-    if (avail < ws_est + reserve + min_planes) return -1;
-    const size_t budget = avail - ws_est - reserve;
+    const size_t plane_need = (size_t)nmod * nbf * (((size_t)kdim + 127) / 128 * 128);  // per operand, one pass over k
+    size_t budget = plane_need * nop;
+    const bool have = s.i8.planes_cap[0] >= plane_need && (nop == 1 || s.i8.planes_cap[1] >= plane_need) && s.i8.ws_cap >= ws_est;
+    if (!have) {
+        // (cudaMemGetInfo only when something must grow: in the steady state of an SCF it would be a driver call per build
+        // that now and then waits tens of milliseconds behind the copies of the other stream)
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const size_t held = s.i8.planes_cap[0] + s.i8.planes_cap[1] + s.i8.ws_cap;
+        const size_t reserve = (size_t)1 << 30;
+        const size_t avail = free_b + held;
+        const size_t min_planes = (size_t)nmod * nbf * nop * (size_t)std::min(kdim, 4 * klen);
+        if (avail < ws_est + reserve + min_planes) return -1;
+        budget = std::min(budget, avail - ws_est - reserve);
+    }
     std::string err;
     I8RunInfo info;
     const uint64_t l0 = s.i8.launches;
@@ -770,7 +819,6 @@ int run_kgemm_i8(b200jk* h, Shard& s, const double* T1, const double* T2, int kd
     if (rc == 3) {  // lost a race for the memory: release and let the DMMA arm run
         cudaGetLastError();
         s.i8.release();
-    s.i8h.release();
         return -1;
     }
     if (rc) return fail(h, B200JK_ERR_CUDA, "INT8 K GEMM: %s", err.c_str());
@@ -947,8 +995,8 @@ int ensure_work(b200jk* h, Shard& s, const Task& t, int* qc_out) {
             if (s.Ctr) CK(cudaFree(s.Ctr));
             s.Ctl = s.Ctr = nullptr;
             s.ct_cap = 0;
-            CK(cudaMalloc((void**)&s.Ctl, ct * sizeof(double)));
-            CK(cudaMalloc((void**)&s.Ctr, ct * sizeof(double)));
+            CK(malloc_elastic(h, (void**)&s.Ctl, ct * sizeof(double)));
+            CK(malloc_elastic(h, (void**)&s.Ctr, ct * sizeof(double)));
             s.ct_cap = ct;
         }
         // the pre-gathered C^T (see want_cgather) is claimed before the T buffers size themselves from what is left
@@ -961,7 +1009,8 @@ int ensure_work(b200jk* h, Shard& s, const Task& t, int* qc_out) {
             // need to (re)allocate: budget = user limit or what is free now (+ what we would release)
             size_t free_b = 0, total_b = 0;
             CK(cudaMemGetInfo(&free_b, &total_b));
-            size_t reclaim = (s.T_cap + s.T2_cap) * sizeof(double);
+            // the INT8 scratch is elastic: it is given back (malloc_elastic) when T needs the room
+            size_t reclaim = (s.T_cap + s.T2_cap) * sizeof(double) + s.i8h.arena_cap + s.i8.planes_cap[0] + s.i8.planes_cap[1] + s.i8.ws_cap;
             size_t budget = free_b + reclaim;
             size_t reserve = ((size_t)1 << 30) + ((size_t)1 << 29);  // split-K partials + slack
             budget = budget > reserve ? budget - reserve : 0;
@@ -978,10 +1027,10 @@ int ensure_work(b200jk* h, Shard& s, const Task& t, int* qc_out) {
             if (s.T2) CK(cudaFree(s.T2));
             s.T1 = s.T2 = nullptr;
             s.T_cap = s.T2_cap = 0;
-            CK(cudaMalloc((void**)&s.T1, per_q * qc * sizeof(double)));
+            CK(malloc_elastic(h, (void**)&s.T1, per_q * qc * sizeof(double)));
             s.T_cap = per_q * qc;
             if (two) {
-                CK(cudaMalloc((void**)&s.T2, per_q * qc * sizeof(double)));
+                CK(malloc_elastic(h, (void**)&s.T2, per_q * qc * sizeof(double)));
                 s.T2_cap = per_q * qc;
             }
         } else {
@@ -1052,9 +1101,12 @@ int run_device_K(b200jk* h, Shard& s, const Task& t, const double* const* dCl, c
             double* Kout = (wk ? outW : outK) + i * n2;
             FuseJ fj_store, *fj = nullptr;
             // the density row can ride on either transform of the Ppq tensor: on T1 normally, on T2 when T1 is reused
-            // (INT8 arm with the planes of the whole shard still resident: the conversion the sweep would ride on is skipped)
-            const bool planes_cached = half_want_i8(h, s, o) && qc >= s.nq && i8h_cached(s.i8h, tenL, 0, s.nq, half_moduli(h));
-            if (!wk && t.do_J && dD && dD[i] && can_fuse_j(o) && !planes_cached) {
+            // (INT8 arm whose planes stay resident across builds: the conversion the sweep would ride on is skipped from the
+            // second build on, so the sweep never rides on it -- J then takes the same kernels in every build)
+            bool planes_stay = false;
+            if (!wk && half_want_i8(h, s, o) && half_i8_arena(h, s, t.max_o, std::min(qc, s.nq), op, !one_T, &planes_stay) < 0)
+                planes_stay = false;
+            if (!wk && t.do_J && dD && dD[i] && can_fuse_j(o) && !planes_stay) {
                 const int ldd = round_up((int)N, 2);
                 fj_store.Dm = s.Dm + (size_t)i * N * ldd;
                 fj_store.ldd = ldd;
@@ -1075,11 +1127,11 @@ int run_device_K(b200jk* h, Shard& s, const Task& t, const double* const* dCl, c
                     if (reuse_T1) {
                         s.skipped_q += nqc;
                         s.skipped_qo += (double)nqc * o;
-                    } else if ((rc = run_half(h, s, tenL, s.Ctl, ldc, o, op, qb, nqc, s.T1, fj, t.max_o))) {
+                    } else if ((rc = run_half(h, s, tenL, s.Ctl, ldc, o, op, qb, nqc, s.T1, fj, t.max_o, !one_T))) {
                         return rc;
                     }
                     FuseJ* fj2 = reuse_T1 ? fj : nullptr;
-                    if (!one_T && (rc = run_half(h, s, tenR, s.Ctr, ldc, o, op, qb, nqc, s.T2, fj2, t.max_o))) return rc;
+                    if (!one_T && (rc = run_half(h, s, tenR, s.Ctr, ldc, o, op, qb, nqc, s.T2, fj2, t.max_o, true))) return rc;
                 }
                 {
                     PhaseScope ps(s, 2);
@@ -1288,6 +1340,7 @@ void free_shard(Shard& s) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     s.i8.release();
+    s.i8h.release();
     for (auto e : s.evpool) cudaEventDestroy(e);
     for (auto e : s.fit_raw_free)
         if (e) cudaEventDestroy(e);
@@ -1312,7 +1365,7 @@ int alloc_tensor(b200jk* h, int which) {
                         "in-core tensor needs %.2f GiB on device %d but only %.2f GiB are free "
                         "(no out-of-core / CPU fallback; use more GPUs)",
                         need / 1073741824.0, s.dev, free_b / 1073741824.0);
-        CK(cudaMalloc((void**)&s.tensor[which], std::max<size_t>(need, 8)));
+        CK(malloc_elastic(h, (void**)&s.tensor[which], std::max<size_t>(need, 8)));
         CK(cudaMemsetAsync(s.tensor[which], 0, need, s.stream));
         // one TMA descriptor per row-block m: dims {sp(m), nq}, row pitch ld(m) doubles
         std::vector<CUtensorMap> maps(h->nbf);
@@ -2052,7 +2105,7 @@ int b200jk_compute_device(b200jk_t* h, int nmat, const double* const* dCl, const
 int b200jk_dev_alloc(b200jk_t* h, size_t bytes, void** dptr) {
     if (!h || !dptr || h->sh.empty()) return B200JK_ERR_INVALID;
     CK(cudaSetDevice(h->sh[0].dev));
-    CK(cudaMalloc(dptr, std::max<size_t>(bytes, 8)));
+    CK(malloc_elastic(h, dptr, std::max<size_t>(bytes, 8)));
     return 0;
 }
 int b200jk_dev_free(b200jk_t* h, void* dptr) {

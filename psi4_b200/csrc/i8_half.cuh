@@ -72,71 +72,83 @@ struct I8HalfFuseJ {
 };
 
 // ---- residue planes of a chunk of row-blocks ------------------------------------------------------------------
-// one warp per row (m0 + mloc, qbeg + q).  Tile (m, t, kb) of plane j lies at
-//   planes + j * plane_stride + ((kboff[m] - kboff[m0]) * nqt + t * nkb(m) + kb) * 16 KB,
+// grid (ceil(qc / 32), nmc): one CTA = 32 rows q of one row-block m, one warp = four of them in turn.  Tile (m, t, kb) of
+// plane j lies at  planes + j * plane_stride + ((kboff[m] - kboff[m0]) * nqt + t * nkb(m) + kb) * 16 KB,
 // row r = q % 128 at r * 128, 16-byte chunk c of the row at chunk c ^ (r & 7) (TMA SWIZZLE_128B order).
+// Fused first J sweep: the density row of m, gathered along the kept-partner list, is staged in shared memory once per
+// CTA (gathering it per row through the LSU cost 20 ms of the 62 the C60 conversion took; the sweep it replaces costs 7.5).
+constexpr int I8H_ROWS = 32;
 template <int NMOD>
 __global__ void __launch_bounds__(256) i8h_convert_kernel(const double* __restrict__ tensor, const size_t* __restrict__ row_off,
                                                           const int* __restrict__ ldm, const int* __restrict__ sp,
                                                           const int* __restrict__ kboff, const int* __restrict__ expo, int nq, int m0,
-                                                          int nmc, int qbeg, int qc, int nqt, int8_t* __restrict__ planes,
-                                                          size_t plane_stride, const I8HalfFuseJ fj) {
-    const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (gw >= (long)nmc * qc) return;
-    const int mloc = (int)(gw / qc), q = (int)(gw - (long)mloc * qc);
-    const int m = m0 + mloc;
+                                                          int qbeg, int qc, int nqt, int8_t* __restrict__ planes, size_t plane_stride,
+                                                          const I8HalfFuseJ fj) {
+    extern __shared__ double i8h_dg[];  // [nkb(m) * 128] density row in the tensor's column order, zero beyond sp(m)
+    const int m = m0 + blockIdx.y;
     const int K = sp[m], nk = kboff[m + 1] - kboff[m];
-    const int t = q >> 7, r = q & 127;
-    const double* src = tensor + row_off[m] + (size_t)(qbeg + q) * ldm[m];
-    int8_t* dst = planes + ((size_t)(kboff[m] - kboff[m0]) * nqt + (size_t)t * nk) * I8H_TILE + r * I8_BK +
-                  (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool fuse = fj.Dm != nullptr;
+    if (fuse) {
+        const double* drow = fj.Dm + (size_t)m * fj.ldd;
+        const int* cm = fj.cols + fj.cols_off[m];
+        for (int k = threadIdx.x; k < nk * I8_BK; k += 256) i8h_dg[k] = k < K ? drow[__ldg(cm + k)] : 0.0;
+        __syncthreads();
+    }
     const double CM = 6755399441055744.0;  // 1.5 * 2^52 (see i8_convert_kernel: one FP64 FMA per element and modulus)
-    const double scale = ldexp(1.0, expo[(size_t)m * nq + qbeg + q]);
-    int k = 4 * lane;
-    double2 a = make_double2(0.0, 0.0), b = a;
-    if (k < K) {
-        a = *reinterpret_cast<const double2*>(src + k);
-        b = *reinterpret_cast<const double2*>(src + k + 2);
-    }
-    const double* drow = fj.Dm ? fj.Dm + (size_t)m * fj.ldd : nullptr;
-    const int* cm = fj.Dm ? fj.cols + fj.cols_off[m] : nullptr;
-    double dq = 0.0;
-    for (int kb = 0; kb < nk; kb++, k += 128) {
-        double y[4] = {a.x, a.y, b.x, b.y};
-        if (drow) {
-#pragma unroll
-            for (int c = 0; c < 4; c++)
-                if (k + c < K) dq = fma(y[c], drow[__ldg(cm + k + c)], dq);
+    const size_t tile0 = (size_t)(kboff[m] - kboff[m0]) * nqt;
+    for (int rr = warp; rr < I8H_ROWS; rr += 8) {
+        const int q = blockIdx.x * I8H_ROWS + rr;
+        if (q >= qc) break;
+        const int t = q >> 7, r = q & 127;
+        const double* src = tensor + row_off[m] + (size_t)(qbeg + q) * ldm[m];
+        int8_t* dst = planes + (tile0 + (size_t)t * nk) * I8H_TILE + r * I8_BK + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2);
+        const double scale = ldexp(1.0, expo[(size_t)m * nq + qbeg + q]);
+        int k = 4 * lane;
+        double2 a = make_double2(0.0, 0.0), b = a;
+        if (k < K) {
+            a = *reinterpret_cast<const double2*>(src + k);
+            b = *reinterpret_cast<const double2*>(src + k + 2);
         }
-        a = make_double2(0.0, 0.0);
-        b = a;
-        if (k + 128 < K) {  // the next 32 bytes of the lane are requested before the current ones are converted
-            a = *reinterpret_cast<const double2*>(src + k + 128);
-            b = *reinterpret_cast<const double2*>(src + k + 130);
+        double dq = 0.0;
+        for (int kb = 0; kb < nk; kb++, k += 128) {
+            double y[4] = {a.x, a.y, b.x, b.y};
+            a = make_double2(0.0, 0.0);
+            b = a;
+            if (k + 128 < K) {  // the next 32 bytes of the lane are requested before the current ones are converted
+                a = *reinterpret_cast<const double2*>(src + k + 128);
+                b = *reinterpret_cast<const double2*>(src + k + 130);
+            }
+            if (fuse) {
+                const double2 d0 = *reinterpret_cast<const double2*>(i8h_dg + k), d1 = *reinterpret_cast<const double2*>(i8h_dg + k + 2);
+                dq = fma(y[0], d0.x, dq);
+                dq = fma(y[1], d0.y, dq);
+                dq = fma(y[2], d1.x, dq);
+                dq = fma(y[3], d1.y, dq);
+            }
+            int ylo[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                y[c] = __dadd_rn(__fma_rn(y[c], scale, CM), -CM);
+                ylo[c] = __double2loint(__dadd_rn(y[c], CM));
+            }
+            int8_t* d = dst + (size_t)kb * I8H_TILE;
+            *reinterpret_cast<uint32_t*>(d) = i8_pack_bytes(ylo[0], ylo[1], ylo[2], ylo[3]);
+#pragma unroll
+            for (int j = 1; j < NMOD; j++) {
+                const int pj = c_i8.p[j];
+                const double inv = c_i8.invpd[j];
+                int rv[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) rv[c] = ylo[c] - pj * __double2loint(__fma_rn(y[c], inv, CM));
+                *reinterpret_cast<uint32_t*>(d + (size_t)j * plane_stride) = i8_pack_bytes(rv[0], rv[1], rv[2], rv[3]);
+            }
         }
-        int ylo[4];
+        if (fuse) {
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            y[c] = __dadd_rn(__fma_rn(y[c], scale, CM), -CM);
-            ylo[c] = __double2loint(__dadd_rn(y[c], CM));
+            for (int w = 16; w > 0; w >>= 1) dq += __shfl_xor_sync(0xffffffffu, dq, w);
+            if (lane == 0) fj.dpart[(size_t)m * fj.dstride + qbeg + q] = dq;
         }
-        int8_t* d = dst + (size_t)kb * I8H_TILE;
-        *reinterpret_cast<uint32_t*>(d) = i8_pack_bytes(ylo[0], ylo[1], ylo[2], ylo[3]);
-#pragma unroll
-        for (int j = 1; j < NMOD; j++) {
-            const int pj = c_i8.p[j];
-            const double inv = c_i8.invpd[j];
-            int rr[4];
-#pragma unroll
-            for (int c = 0; c < 4; c++) rr[c] = ylo[c] - pj * __double2loint(__fma_rn(y[c], inv, CM));
-            *reinterpret_cast<uint32_t*>(d + (size_t)j * plane_stride) = i8_pack_bytes(rr[0], rr[1], rr[2], rr[3]);
-        }
-    }
-    if (drow) {
-#pragma unroll
-        for (int w = 16; w > 0; w >>= 1) dq += __shfl_xor_sync(0xffffffffu, dq, w);
-        if (lane == 0) fj.dpart[(size_t)m * fj.dstride + qbeg + q] = dq;
     }
 }
 
@@ -451,6 +463,7 @@ __global__ void __launch_bounds__(256) i8h_crt_kernel(const I8HalfCrtParams p) {
 struct I8HalfPlan {  // per shard
     // k-blocks per row-block (from the engine's tables, at set_layout): nkb(m) = ceil(sp(m) / 128), kboff = running sum
     std::vector<int> kboff;  // [nbf + 1]
+    int max_nkb_row = 0;     // largest nkb(m)
     int* d_kboff = nullptr;
     // scales of the tensor rows, per tensor; valid until the tensor changes
     int* expoB[3] = {nullptr, nullptr, nullptr};
@@ -503,7 +516,11 @@ inline int i8h_set_layout(I8HalfPlan& pl, const std::vector<int>& sp, std::strin
     const size_t nbf = sp.size();
     pl.kboff.resize(nbf + 1);
     pl.kboff[0] = 0;
-    for (size_t m = 0; m < nbf; m++) pl.kboff[m + 1] = pl.kboff[m] + (sp[m] + I8_BK - 1) / I8_BK;
+    pl.max_nkb_row = 0;
+    for (size_t m = 0; m < nbf; m++) {
+        pl.kboff[m + 1] = pl.kboff[m] + (sp[m] + I8_BK - 1) / I8_BK;
+        pl.max_nkb_row = std::max(pl.max_nkb_row, pl.kboff[m + 1] - pl.kboff[m]);
+    }
     if (pl.d_kboff) cudaFree(pl.d_kboff);
     pl.d_kboff = nullptr;
     I8CK(cudaMalloc((void**)&pl.d_kboff, (nbf + 1) * sizeof(int)));
@@ -526,10 +543,10 @@ inline bool i8h_cached(const I8HalfPlan& pl, int which, int qbeg, int qc, int nm
 template <int NMOD>
 inline void i8h_launch_convert(const double* tensor, const size_t* row_off, const int* ldm, const int* sp, const int* kboff,
                                const int* expo, int nq, int m0, int nmc, int qbeg, int qc, int nqt, int8_t* planes, size_t plane_stride,
-                               const I8HalfFuseJ& fj, cudaStream_t st) {
-    const long warps = (long)nmc * qc;
-    i8h_convert_kernel<NMOD><<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(tensor, row_off, ldm, sp, kboff, expo, nq, m0, nmc, qbeg, qc, nqt,
-                                                                         planes, plane_stride, fj);
+                               const I8HalfFuseJ& fj, int max_nkb, cudaStream_t st) {
+    const size_t smem = fj.Dm ? (size_t)max_nkb * I8_BK * sizeof(double) : 0;
+    i8h_convert_kernel<NMOD><<<dim3((unsigned)((qc + I8H_ROWS - 1) / I8H_ROWS), (unsigned)nmc), 256, smem, st>>>(
+        tensor, row_off, ldm, sp, kboff, expo, nq, m0, qbeg, qc, nqt, planes, plane_stride, fj);
 }
 template <int NMOD>
 inline void i8h_launch_crt(const I8HalfCrtParams& p, int nmc, cudaStream_t st) {
@@ -678,14 +695,18 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
     };
     std::vector<Chunk> chunks;
     size_t max_nkb = 0, max_nm = 0;
-    {
+    // the three regions are carved at the maxima over the chunks (planes and C^T by k-blocks, residues by row-blocks), which
+    // different chunks may attain: plan against a budget and shrink it until the carve fits
+    for (size_t budget = pl.arena_cap;; budget -= budget / 16) {
+        chunks.clear();
+        max_nkb = max_nm = 0;
         const size_t slack = 65536;
         int m0 = 0;
         size_t nkb = 0, cost = slack;
         for (int m = 0; m < nbf; m++) {
             const int nk = pl.kboff[m + 1] - pl.kboff[m];
             const size_t c = std::max(i8h_cost(nmod, nk, nqt, qc, nit_p, ntile_p), i8h_cost(nmod, nk, nqt, qc, nit, ntile_n));
-            if (m > m0 && cost + c > pl.arena_cap) {
+            if (m > m0 && cost + c > budget) {
                 chunks.push_back(Chunk{m0, m, nkb});
                 m0 = m;
                 nkb = 0;
@@ -693,7 +714,7 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
             }
             nkb += (size_t)nk;
             cost += c;
-            if (cost > pl.arena_cap) {
+            if (cost > budget) {
                 if (err) *err = "scratch arena too small for one row-block of residue planes";
                 return 3;
             }
@@ -703,6 +724,8 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
             max_nkb = std::max(max_nkb, c.nkb);
             max_nm = std::max(max_nm, (size_t)(c.m1 - c.m0));
         }
+        const size_t carve = (size_t)nmod * (max_nkb * ((size_t)nqt * I8H_TILE + (size_t)nit * ntile_n * I8_BK) + max_nm * (size_t)qc * opw);
+        if (carve <= pl.arena_cap) break;
     }
     const size_t plane_stride = max_nkb * (size_t)nqt * I8H_TILE;
     const size_t cg_plane = max_nkb * (size_t)nit * ntile_n * I8_BK;
@@ -734,7 +757,7 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
         }
         if (!cached)
             I8H_DISPATCH(nmod, i8h_launch_convert, tensor, d_row_off, d_ldm, d_sp, pl.d_kboff, pl.expoB[which], nq, c.m0, nmc, qbeg, qc, nqt,
-                         planes, plane_stride, fjv, st);
+                         planes, plane_stride, fjv, pl.max_nkb_row, st);
         if (prof) cudaEventRecord(pl.prof[1], st);
         i8h_gather_kernel<<<dim3((unsigned)nmc, (unsigned)((opw + 3) / 4)), 128, 0, st>>>(pl.rc, rc_ld, rc_plane, o, nmod, d_sp, pl.d_kboff, d_cols,
                                                                                         d_cols_off, c.m0, nit, ntile_n, cg, cg_plane);

@@ -112,8 +112,9 @@ int main(int argc, char** argv) {
     for (int m = 0; m < nbf; m++) {
         cols_off[m] = cols.size();
         for (int n = 0; n < nbf; n++) {
-            const uint64_t h = mix64(((uint64_t)std::min(m, n) << 32) | (uint64_t)std::max(m, n));
-            const bool keep = m == n || (double)(h >> 11) * (1.0 / 9007199254740992.0) < density;
+            const int bm = m / 6, bn = n / 6;  // shells of six functions: kept partners come in runs, as in a real pair mask
+            const uint64_t h = mix64(((uint64_t)std::min(bm, bn) << 32) | (uint64_t)std::max(bm, bn));
+            const bool keep = bm == bn || (double)(h >> 11) * (1.0 / 9007199254740992.0) < density;
             if (keep) cols.push_back(n);
         }
         sp[m] = (int)(cols.size() - cols_off[m]);
@@ -189,9 +190,9 @@ int main(int argc, char** argv) {
         CK(cudaEventElapsedTime(&ms, e0, e1));
         if (r > 0 && ms < best) best = ms;  // the first call also computes the row scales of the tensor
         for (int i = 0; i < 4; i++) {
-            float t;
-            CK(cudaEventElapsedTime(&t, pl.prof[i], pl.prof[i + 1]));
-            if (t < bp[i]) bp[i] = t;
+            float t = 0;
+            if (cudaEventElapsedTime(&t, pl.prof[i], pl.prof[i + 1]) != cudaSuccess) cudaGetLastError();
+            if (r > 0 && t < bp[i]) bp[i] = t;
         }
     }
     const double flops = 2.0 * nq * (double)cols.size() * o;

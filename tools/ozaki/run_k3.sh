@@ -1,7 +1,7 @@
 #!/bin/bash
 cd tools/ozaki
-for args in "300 500 37 0.7 12 1.0 1 2" "300 500 37 0.7 13 0.05 1 4" "200 300 300 1.0 12 1.0 1 4" "257 131 5 0.3 12 1.0 1 4" "1800 1185 180 0.715 12 8 2 1" "1800 1185 180 0.715 12 8 2 2" "1800 1185 180 0.715 12 8 2 4"; do
+for args in "300 500 37 0.7 12 1.0 1 2" "1800 1185 180 0.715 12 8 2 1" "1800 4740 180 0.715 12 50 2 1" "1800 592 180 0.715 12 50 3 1" "1800 592 180 0.715 12 50 3 2"; do
   echo "== $args"
-  timeout 60 ./k3_i8_test $args 2>&1 | tail -5
+  timeout 100 ./k3_i8_test $args 2>&1 | tail -5
   echo "rc=$?"
 done
