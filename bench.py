@@ -368,18 +368,23 @@ def measure(args, ds, name, steps, warmup, headline):
     w0 = time.perf_counter()
     dev_ms, parts = 0.0, {"ms_j": 0.0, "ms_half": 0.0, "ms_kgemm": 0.0, "ms_allreduce": 0.0}
     launches = 0
+    sub = {"ms_half_i8": [0.0] * 4, "ms_kgemm_i8": [0.0] * 3}  # sub-phases of the INT8 arms (zero on the DMMA arms)
     for _ in range(steps):
         eng.compute_device(dC, dCr, noccs, dD, dJ, dK, None)
         st = eng.stats()
         dev_ms += st["ms_total"]
         for k in parts:
             parts[k] += st[k]
+        for k in sub:
+            sub[k] = [a + b for a, b in zip(sub[k], st[k])]
         launches += st["launches"]
     ds.barrier()
     wall_ms = ds.max((time.perf_counter() - w0) * 1e3 / steps)
     value = ds.max(dev_ms / steps)
     for k in parts:
         parts[k] = ds.max(parts[k] / steps)
+    for k in sub:
+        sub[k] = [ds.max(x / steps) for x in sub[k]]
     st_dev = eng.stats()
 
     # ---- end-to-end arm: host pointers through b200jk_compute ----
@@ -472,12 +477,62 @@ def measure(args, ds, name, steps, warmup, headline):
     reduce_kind = {0: "none (one GPU)", 1: "fixed-rank-order peer-memory kernel over NVLink (peer_reduce.cuh)",
                    2: "NCCL all-reduce"}.get(st_dev["reduce_kind"], "?")
     eng.close()
-    res = dict(cfg=cfg, keep=keep, amp=amp, Cl=Cl, Crl=Crl, value=value, wall_ms=wall_ms, parts=parts, st_dev=st_dev,
+    res = dict(cfg=cfg, keep=keep, amp=amp, Cl=Cl, Crl=Crl, value=value, wall_ms=wall_ms, parts=parts, sub=sub, st_dev=st_dev,
                e2e_ms=e2e_ms, e2e_parts=e2e_parts, launches=launches, clk=clk, arms_equal=bool(arms_equal), arms_diff=arms_diff,
                run_equal=bool(run_equal), ranks_equal=bool(ranks_equal), spot=spot, pk_dmma=pk_dmma, pk_dfma=pk_dfma,
                layout_s=layout_s, fill_s=fill_s, reduce_kind=reduce_kind, setup=setup, fp64_arms=fp64_arms,
                h2d=int(nmat * (Cl[0].nbytes * (1 if Crl is None else 2) + n2b)), d2h=int(nmat * 2 * n2b))
     return res
+
+
+def int8_peak():
+    """INT8 dense tensor ceiling for the residue GEMMs.  MEASURED_PEAKS.json holds no int8 figure; on this part the dense
+    int8 rate of tcgen05.mma is twice the bf16 one (4.5 vs 2.25 Pop/s nominal), so the ceiling is 2 x the MEASURED bf16
+    numbers: sustained for kernels timed inside a long step (B200_PROFILING.md), burst beside it."""
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return {"sustained_tops": 2.0 * float(mp.get("bf16_tflops_sustained", mp["bf16_tflops"])), "burst_tops": 2.0 * float(mp["bf16_tflops"]),
+                "source": "2 x MEASURED_PEAKS.json bf16 (sustained / burst); no int8 entry there"}
+    except Exception:
+        return {"sustained_tops": 4500.0, "burst_tops": 4500.0, "source": "nominal 4.5 Pop/s dense int8 (MEASURED_PEAKS.json absent)"}
+
+
+def i8_table(res, hbm_peak):
+    """Sub-phases of the INT8-tensor-core arms of the timed builds (CUDA events between their launches): every one with the
+    roofline that bounds it -- the converter and the CRT are streaming kernels (HBM), the two GEMMs tensor work whose
+    operands (residue planes) also come from HBM, so both views are given."""
+    st, sub = res["st_dev"], res["sub"]
+    pk = int8_peak()
+    out = {}
+    if st.get("half_kind"):
+        cv, ga, ge, cr = sub["ms_half_i8"]
+        cfg = res["cfg"]
+        t_bytes = 8.0 * cfg["nbf"] * (st["q_end"] - st["q_begin"]) * (cfg["nocc"] + cfg["nocc"] % 2) * cfg["nmat"] * (1 if res["Crl"] is None else 2)
+        out["half_transform"] = {
+            "moduli": st["half_moduli"], "chunks": st["half_i8_chunks"], "planes_cached": st["half_i8_cached"],
+            "convert": {"ms": cv, "bound": "hbm", "bytes": st["half_i8_convert_bytes"],
+                        "gbs": st["half_i8_convert_bytes"] / (cv * 1e-3) / 1e9 if cv else 0.0,
+                        "frac_of_hbm_peak": st["half_i8_convert_bytes"] / (cv * 1e-3) / 1e9 / hbm_peak if cv else None,
+                        "what": "f64 rows read + residue planes written (+ the first J sweep riding on it)"},
+            "gather": {"ms": ga},
+            "gemm": {"ms": ge, "bound": "tensor", "int8_tops": st["half_i8_ops"] / (ge * 1e-3) / 1e12 if ge else 0.0,
+                     "frac_of_int8_peak": st["half_i8_ops"] / (ge * 1e-3) / 1e12 / pk["sustained_tops"] if ge else None,
+                     "plane_read_gbs": st["half_i8_plane_bytes"] / (ge * 1e-3) / 1e9 if ge else 0.0,
+                     "frac_of_hbm_peak": st["half_i8_plane_bytes"] / (ge * 1e-3) / 1e9 / hbm_peak if ge else None,
+                     "what": "tcgen05.mma.kind::i8 over all moduli, whole padded tiles; A planes streamed once from HBM"},
+            "crt": {"ms": cr, "bound": "hbm", "t_write_gbs": t_bytes / (cr * 1e-3) / 1e9 if cr else 0.0},
+        }
+    if st.get("kgemm_kind"):
+        pl, ge, cr = sub["ms_kgemm_i8"]
+        out["k_gemm"] = {
+            "moduli": st["kgemm_moduli"], "planes": {"ms": pl, "bound": "hbm"},
+            "gemm": {"ms": ge, "bound": "tensor", "int8_tops": st["kgemm_i8_ops"] / (ge * 1e-3) / 1e12 if ge else 0.0,
+                     "frac_of_int8_peak": st["kgemm_i8_ops"] / (ge * 1e-3) / 1e12 / pk["sustained_tops"] if ge else None},
+            "crt": {"ms": cr},
+        }
+    if out:
+        out["int8_peak"] = pk
+    return out
 
 
 def kernel_table(res, peak_dmma, hbm_peak, peak_src):
@@ -486,7 +541,7 @@ def kernel_table(res, peak_dmma, hbm_peak, peak_src):
     kg_tf = st["kgemm_flops"] / (parts["ms_kgemm"] * 1e-3) / 1e12 if parts["ms_kgemm"] else 0.0
     j_gbs = st["j_bytes"] / (parts["ms_j"] * 1e-3) / 1e9 if parts["ms_j"] else 0.0
     arm = {0: "FP64 tensor pipe (DMMA m8n8k4)", 1: "INT8 tensor cores (tcgen05.mma.kind::i8) by residues + CRT; tflops = FP64-equivalent"}
-    return {
+    kt = {
         "half_transform": {"ms": parts["ms_half"], "tflops": half_tf, "arm": arm[st.get("half_kind", 0)],
                            "frac_of_dmma_peak": half_tf / peak_dmma if peak_dmma else None,
                            "hbm_read_gbs": st["half_bytes"] / (parts["ms_half"] * 1e-3) / 1e9 if parts["ms_half"] else 0.0},
@@ -495,7 +550,14 @@ def kernel_table(res, peak_dmma, hbm_peak, peak_src):
         "j_sweeps": {"ms": parts["ms_j"], "gbs": j_gbs, "frac_of_hbm_peak": j_gbs / hbm_peak, "hbm_peak_gbs": hbm_peak,
                      "hbm_peak_source": peak_src},
         "cross_gpu_sum": {"ms": parts["ms_allreduce"], "how": res["reduce_kind"]},
-    }, half_tf
+    }
+    i8 = i8_table(res, hbm_peak)
+    for k in ("half_transform", "k_gemm"):
+        if k in i8:
+            kt[k]["int8_arm"] = i8[k]
+    if i8:
+        kt["int8_peak"] = i8["int8_peak"]
+    return kt, half_tf
 
 
 def single_process(args, cfg_name):
@@ -622,13 +684,37 @@ def main():
         ab["half_transform_frac_of_dmma_peak"] = ab["half_transform_tflops"] / peak_dmma if peak_dmma else None
         ab["k_gemm_frac_of_dmma_peak"] = ab["k_gemm_tflops"] / peak_dmma if peak_dmma else None
         ab["what"] = "the same build with both GEMMs on the FP64 tensor pipe (B200JK_KGEMM=dmma B200JK_HALF=dmma), 3 device-resident builds"
-    roofline = {"kernel": "half_ws_kernel (K3)", "bound": "tensor", "achieved": half_tf, "peak": peak_dmma,
-                "unit": "TFLOP/s", "frac": half_tf / peak_dmma if peak_dmma else None, "traffic": traffic,
-                "traffic_source": "profiles/traffic.json (ncu --set full capture of this kernel, recorded, not re-measured in this run)",
-                "peak_source": "sustained FP64 DMMA m8n8k4 register-resident loop (1.5 s back to back) measured live "
-                               "on this GPU; no FP64 entry in MEASURED_PEAKS.json; datasheet 37-40 TFLOP/s",
-                "peak_burst": pk_dmma["burst_tflops"], "frac_of_burst": half_tf / pk_dmma["burst_tflops"] if pk_dmma["burst_tflops"] else None,
-                "dmma_probe": pk_dmma, "dfma_probe": pk_dfma}
+    roofline_fp64 = {"kernel": "half_ws_kernel (K3, FP64 tensor pipe)", "bound": "tensor", "achieved": half_tf, "peak": peak_dmma,
+                     "unit": "TFLOP/s", "frac": half_tf / peak_dmma if peak_dmma else None, "traffic": traffic,
+                     "traffic_source": "profiles/traffic.json (ncu --set full capture of this kernel, recorded, not re-measured in this run)",
+                     "peak_source": "sustained FP64 DMMA m8n8k4 register-resident loop (1.5 s back to back) measured live "
+                                    "on this GPU; no FP64 entry in MEASURED_PEAKS.json; datasheet 37-40 TFLOP/s",
+                     "peak_burst": pk_dmma["burst_tflops"], "frac_of_burst": half_tf / pk_dmma["burst_tflops"] if pk_dmma["burst_tflops"] else None,
+                     "dmma_probe": pk_dmma, "dfma_probe": pk_dfma,
+                     "measured_in": "the fp64_arms A/B builds of this run" if (ab and res["st_dev"]["half_kind"]) else "the timed region"}
+    # `roofline` is the DOMINANT kernel of the timed builds.  On the FP64 arms that is K3 on the DMMA pipe; when the default
+    # arms ran on the INT8 tensor cores it is whichever sub-phase of them took longest, with its own bound and ceiling.
+    roofline = roofline_fp64
+    i8h = kernels["half_transform"].get("int8_arm")
+    if i8h:
+        cands = [("i8h_convert_kernel (f64 rows -> residue planes, first J sweep fused)", i8h["convert"]["ms"], "hbm"),
+                 ("i8h_gemm_kernel (tcgen05.mma.kind::i8, cluster-multicast, TMEM accumulators)", i8h["gemm"]["ms"], "tensor")]
+        i8k = kernels["k_gemm"].get("int8_arm")
+        if i8k:
+            cands.append(("i8_pipeline_kernel (K GEMM, tcgen05.mma.kind::i8)", i8k["gemm"]["ms"], "tensor_k"))
+        name, ms, kind = max(cands, key=lambda c: c[1])
+        pk8 = kernels["int8_peak"]
+        if kind == "hbm":
+            roofline = {"kernel": name, "bound": "hbm", "achieved": i8h["convert"]["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                        "frac": i8h["convert"]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes": i8h["convert"]["bytes"], "ms": ms}
+        else:
+            g = i8h["gemm"] if kind == "tensor" else i8k["gemm"]
+            roofline = {"kernel": name, "bound": "tensor", "achieved": g["int8_tops"], "peak": pk8["sustained_tops"], "unit": "TOP/s (int8)",
+                        "frac": g["frac_of_int8_peak"], "traffic": None, "peak_source": pk8["source"], "ms": ms}
+        roofline["share_of_build"] = ms / res["value"] if res["value"] else None
+        roofline["note"] = ("dominant kernel of the default (INT8-tensor-core) build; the FP64 tensor-pipe roofline the north_star "
+                            "names is `roofline_fp64`")
 
     cfg = res["cfg"]
     if world == 1 and not args.no_extra:
@@ -659,7 +745,7 @@ def main():
         "data": "synthetic", "config": config_of(args.workload, cfg, res["keep"], res["Crl"]),
         "e2e": {"value": res["e2e_ms"], "unit": "ms", "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"],
                 "ms_h2d": res["e2e_parts"]["ms_h2d"], "ms_d2h": res["e2e_parts"]["ms_d2h"]},
-        "gpu_launches": int(res["launches"]), "roofline": roofline, "cpu_baseline": cb, "kernels": kernels, "clocks": res["clk"],
+        "gpu_launches": int(res["launches"]), "roofline": roofline, "roofline_fp64": roofline_fp64, "cpu_baseline": cb, "kernels": kernels, "clocks": res["clk"],
         "wall_ms_per_step": res["wall_ms"], "arms_bit_identical": res["arms_equal"], "arms_diff": res["arms_diff"],
         "run_to_run_bit_identical": res["run_equal"], "ranks_bit_identical": res["ranks_equal"],
         "parity_spot": res["spot"], "workloads": wl,

@@ -207,6 +207,18 @@ typedef struct {
     int kgemm_kind;       /* arm the K GEMM took: 0 FP64 tensor pipe (DMMA), 1 INT8 tensor cores by residues       */
     int kgemm_moduli;     /* moduli of the residue arm (13: 50 bits below the row norm)                            */
     int half_kind;        /* arm the half transform took: 0 FP64 tensor pipe (DMMA), 1 INT8 tensor cores by residues */
+    /* sub-phases of the INT8 arms (CUDA events between their launches, max over local shards; zero on the DMMA arms) */
+    double ms_half_i8[4];  /* conversion to residue planes (+ fused first J sweep), C^T gather, tcgen05 GEMM, CRT    */
+    double ms_kgemm_i8[3]; /* row scales + residue planes of T, tcgen05 GEMM, CRT                                    */
+    double half_i8_ops;    /* 2 x int8 multiply-adds the half transform issued to the tensor cores (all moduli,
+                              whole padded tiles), this handle's shards                                              */
+    double half_i8_plane_bytes;   /* residue-plane bytes its GEMM read                                               */
+    double half_i8_convert_bytes; /* bytes the conversions that RAN moved: f64 rows read + planes written (0: cached) */
+    double kgemm_i8_ops;   /* the same count for the K GEMM                                                          */
+    int half_moduli;       /* moduli of the half transform's residue arm (12: 47 bits below |B row| |C column|)      */
+    int half_i8_chunks;    /* row-block chunks the scratch arena forced (summed over transforms)                     */
+    int half_i8_cached;    /* transforms that found their residue planes cached from an earlier build                */
+    int reserved_;
 } b200jk_stats;
 
 int b200jk_get_stats(const b200jk_t* h, b200jk_stats* out);

@@ -165,6 +165,10 @@ struct Shard {
     int half_kind = 0;  // arm the last half transform of the current build took (0 DMMA, 1 INT8 residues)
     int kgemm_kind = 0, kgemm_moduli = 0;  // arm the last K GEMM of the current build took (0 DMMA, 1 INT8 residues)
     int j_reads = 0;  // passes over the tensor the J sweeps of the current build made (first sweeps + batched second sweeps)
+    // sub-phases of the INT8 arms of the current build: (tag, event) in stream order (tags: i8_half.cuh / i8_kgemm.cuh `mark`)
+    std::vector<std::pair<int, cudaEvent_t>> marks;
+    double i8h_ops = 0, i8h_plane_bytes = 0, i8h_convert_bytes = 0, i8k_ops = 0;
+    int i8h_nmod = 0, i8h_chunks = 0, i8h_cached = 0;
 };
 }  // namespace
 
@@ -311,6 +315,13 @@ cudaEvent_t get_event(Shard& s) {
         s.evpool.push_back(e);
     }
     return s.evpool[s.evused++];
+}
+// phase marker handed to the INT8 arms: one event per sub-phase boundary on the compute stream
+void i8_mark(void* ctx, int tag) {
+    Shard& s = *static_cast<Shard*>(ctx);
+    cudaEvent_t e = get_event(s);
+    cudaEventRecord(e, s.stream);
+    s.marks.emplace_back(tag, e);
 }
 struct PhaseScope {
     Shard& s;
@@ -708,12 +719,20 @@ int run_half_i8(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o
         f8.dstride = fj->dstride;
     }
     const uint64_t l0 = s.i8h.launches;
+    s.i8h.mark = i8_mark;
+    s.i8h.mark_ctx = &s;
     int rc = i8_half_run(s.i8h, s.stream, s.nsm, s.tensor[which], which, s.d_row_off, s.d_ldm, s.d_sp, s.d_cols, s.d_cols_off, nbf, s.nq,
                          Ct, ldc, o, op, max_o, qbeg, qc, T, (size_t)qc * op, nmod, cluster, fj ? &f8 : nullptr, &info, &err);
     s.launches += s.i8h.launches - l0;
     if (rc == 3) return -1;
     if (rc) return fail(h, B200JK_ERR_CUDA, "INT8 half transform: %s", err.c_str());
     s.half_kind = 1;
+    s.i8h_ops += info.mma_ops;
+    s.i8h_plane_bytes += info.plane_bytes;
+    s.i8h_convert_bytes += info.convert_bytes;
+    s.i8h_nmod = info.nmod;
+    s.i8h_chunks += info.nchunks;
+    s.i8h_cached += info.cached;
     return 0;
 }
 
@@ -813,6 +832,8 @@ int run_kgemm_i8(b200jk* h, Shard& s, const double* T1, const double* T2, int kd
     std::string err;
     I8RunInfo info;
     const uint64_t l0 = s.i8.launches;
+    s.i8.mark = i8_mark;
+    s.i8.mark_ctx = &s;
     int rc = i8_kgemm_run(s.i8, (I8EncodeFn)g_encode, s.stream, s.nsm, T1, T2, (size_t)kdim, nbf, kdim, symmetric, Kout, nbf, nmod,
                           klen, budget, &info, &err);
     s.launches += s.i8.launches - l0;
@@ -824,6 +845,7 @@ int run_kgemm_i8(b200jk* h, Shard& s, const double* T1, const double* T2, int kd
     if (rc) return fail(h, B200JK_ERR_CUDA, "INT8 K GEMM: %s", err.c_str());
     s.kgemm_kind = 1;
     s.kgemm_moduli = info.nmod;
+    s.i8k_ops += info.mma_ops;
     return 0;
 }
 
@@ -1188,7 +1210,30 @@ int collect_stats(b200jk* h) {
     b200jk_stats& st = h->stats;
     st.ms_total = st.ms_j = st.ms_half = st.ms_kgemm = st.ms_allreduce = st.ms_h2d = st.ms_d2h = 0;
     st.launches = 0;
+    for (int i = 0; i < 4; i++) st.ms_half_i8[i] = 0;
+    for (int i = 0; i < 3; i++) st.ms_kgemm_i8[i] = 0;
+    st.half_i8_ops = st.half_i8_plane_bytes = st.half_i8_convert_bytes = st.kgemm_i8_ops = 0;
+    st.half_moduli = st.half_i8_chunks = st.half_i8_cached = 0;
     for (auto& s : h->sh) {
+        // sub-phases of the INT8 arms: the time between two consecutive marks belongs to the later one's tag
+        double sub_h[4] = {0, 0, 0, 0}, sub_k[3] = {0, 0, 0};
+        for (size_t i = 1; i < s.marks.size(); i++) {
+            const int tag = s.marks[i].first;
+            if (tag % 10 == 0) continue;  // a chunk / pass starts: what lies before it is not this arm's
+            float ms = 0;
+            cudaEventElapsedTime(&ms, s.marks[i - 1].second, s.marks[i].second);
+            if (tag >= 11 && tag <= 14) sub_h[tag - 11] += ms;
+            if (tag >= 21 && tag <= 23) sub_k[tag - 21] += ms;
+        }
+        for (int i = 0; i < 4; i++) st.ms_half_i8[i] = std::max(st.ms_half_i8[i], sub_h[i]);
+        for (int i = 0; i < 3; i++) st.ms_kgemm_i8[i] = std::max(st.ms_kgemm_i8[i], sub_k[i]);
+        st.half_i8_ops += s.i8h_ops;
+        st.half_i8_plane_bytes += s.i8h_plane_bytes;
+        st.half_i8_convert_bytes += s.i8h_convert_bytes;
+        st.kgemm_i8_ops += s.i8k_ops;
+        st.half_moduli = std::max(st.half_moduli, s.i8h_nmod);
+        st.half_i8_chunks += s.i8h_chunks;
+        st.half_i8_cached += s.i8h_cached;
         double acc[7] = {0, 0, 0, 0, 0, 0, 0};
         for (auto& ph : s.phases) {
             float ms = 0;
@@ -1300,8 +1345,11 @@ int check_compute_args(b200jk* h, int nmat, const int* nocc, bool do_J, bool do_
 void begin_compute(b200jk* h) {
     for (auto& s : h->sh) {
         s.phases.clear();
+        s.marks.clear();
         s.evused = 0;
         s.launches = 0;
+        s.i8h_ops = s.i8h_plane_bytes = s.i8h_convert_bytes = s.i8k_ops = 0;
+        s.i8h_nmod = s.i8h_chunks = s.i8h_cached = 0;
     }
 }
 

@@ -464,6 +464,7 @@ struct I8HalfPlan {  // per shard
     // k-blocks per row-block (from the engine's tables, at set_layout): nkb(m) = ceil(sp(m) / 128), kboff = running sum
     std::vector<int> kboff;  // [nbf + 1]
     int max_nkb_row = 0;     // largest nkb(m)
+    double sum_sp = 0;       // kept pairs (sum of sp(m))
     int* d_kboff = nullptr;
     // scales of the tensor rows, per tensor; valid until the tensor changes
     int* expoB[3] = {nullptr, nullptr, nullptr};
@@ -487,6 +488,10 @@ struct I8HalfPlan {  // per shard
     int cache_which = -1, cache_qbeg = -1, cache_qc = -1, cache_nmod = -1;
     uint64_t conversions_skipped = 0;
     cudaEvent_t prof[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // optional: start / convert / gather / GEMM / CRT of chunk 0
+    // optional phase marker of the caller (the engine records an event on the stream): 10 = a chunk starts, 11 / 12 / 13 / 14 =
+    // its conversion / gather / GEMM / CRT is launched
+    void (*mark)(void* ctx, int tag) = nullptr;
+    void* mark_ctx = nullptr;
     void release_arena() {
         if (arena) cudaFree(arena);
         arena = nullptr;
@@ -517,7 +522,9 @@ inline int i8h_set_layout(I8HalfPlan& pl, const std::vector<int>& sp, std::strin
     pl.kboff.resize(nbf + 1);
     pl.kboff[0] = 0;
     pl.max_nkb_row = 0;
+    pl.sum_sp = 0;
     for (size_t m = 0; m < nbf; m++) {
+        pl.sum_sp += (double)sp[m];
         pl.kboff[m + 1] = pl.kboff[m] + (sp[m] + I8_BK - 1) / I8_BK;
         pl.max_nkb_row = std::max(pl.max_nkb_row, pl.kboff[m + 1] - pl.kboff[m]);
     }
@@ -607,6 +614,9 @@ struct I8HalfInfo {
     int nmod = 0, nchunks = 0, ntile_n = 0, nit = 0, cluster = 0, cached = 0;
     double bits = 0;
     size_t arena = 0;
+    // work of this call: 2 x int8 multiply-adds issued to the tensor cores (all moduli, whole padded tiles), bytes of residue
+    // planes the GEMM read, bytes the conversions that RAN moved (f64 rows read + planes written)
+    double mma_ops = 0, plane_bytes = 0, convert_bytes = 0;
 };
 
 // orbital tiling: nit tiles of ntile_n columns (whole 8-row swizzle atoms per cluster slice), opw = nit * ntile_n >= o
@@ -748,6 +758,7 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
         const int nmc = c.m1 - c.m0;
         const bool prof = pl.prof[0] && nch == 0;
         if (prof) cudaEventRecord(pl.prof[0], st);
+        if (pl.mark) pl.mark(pl.mark_ctx, 10);
         if (cached) pl.conversions_skipped++;
         I8HalfFuseJ fjv = {nullptr, 0, nullptr, 0, nullptr, nullptr};
         if (fuse) {
@@ -759,9 +770,11 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
             I8H_DISPATCH(nmod, i8h_launch_convert, tensor, d_row_off, d_ldm, d_sp, pl.d_kboff, pl.expoB[which], nq, c.m0, nmc, qbeg, qc, nqt,
                          planes, plane_stride, fjv, pl.max_nkb_row, st);
         if (prof) cudaEventRecord(pl.prof[1], st);
+        if (pl.mark) pl.mark(pl.mark_ctx, 11);
         i8h_gather_kernel<<<dim3((unsigned)nmc, (unsigned)((opw + 3) / 4)), 128, 0, st>>>(pl.rc, rc_ld, rc_plane, o, nmod, d_sp, pl.d_kboff, d_cols,
                                                                                         d_cols_off, c.m0, nit, ntile_n, cg, cg_plane);
         if (prof) cudaEventRecord(pl.prof[2], st);
+        if (pl.mark) pl.mark(pl.mark_ctx, 12);
         I8HalfParams gp;
         gp.nmod = nmod;
         gp.nqt = nqt;
@@ -782,6 +795,7 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
                                : (cluster == 2 ? i8h_launch_gemm<2>(gp, nsm, st, err) : i8h_launch_gemm<4>(gp, nsm, st, err))))
             return rc;
         if (prof) cudaEventRecord(pl.prof[3], st);
+        if (pl.mark) pl.mark(pl.mark_ctx, 13);
         I8HalfCrtParams cp;
         cp.ws = ws;
         cp.ws_mod_stride = gp.ws_mod_stride;
@@ -802,6 +816,7 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
         cp.H_hi = (unsigned long long)((M / 2) >> 64);
         I8H_DISPATCH(nmod, i8h_launch_crt, cp, nmc, st);
         if (prof) cudaEventRecord(pl.prof[4], st);
+        if (pl.mark) pl.mark(pl.mark_ctx, 14);
         pl.launches += 4;
         I8CK(cudaGetLastError());
         nch++;
@@ -821,6 +836,10 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
         info->cluster = cluster;
         info->bits = log2(Rb);
         info->arena = pl.arena_cap;
+        const double nkb_all = (double)pl.kboff[nbf];
+        info->mma_ops = 2.0 * nmod * ((double)((nqt + cluster - 1) / cluster * cluster) * I8_TM) * (nkb_all * I8_BK) * ((double)nit * ntile_n);
+        info->plane_bytes = (double)nmod * nqt * nkb_all * I8H_TILE;
+        info->convert_bytes = cached ? 0.0 : 8.0 * qc * pl.sum_sp + info->plane_bytes;
     }
     return 0;
 }

@@ -585,10 +585,15 @@ struct I8Plan {  // per device: buffers grown on demand, kept across builds
     I8Tile* d_tiles = nullptr;
     int* d_counter = nullptr;
     int tiles_nbf = -1, tiles_sym = -1, ntile = 0;
+    double tile_area = 0;  // sum over the tile list of 128 x (padded columns)
     int bbox[3] = {256, 0, 0};
     bool consts = false, attr = false;
     uint64_t launches = 0;
     cudaEvent_t prof[4] = {nullptr, nullptr, nullptr, nullptr};  // optional: start / planes done / GEMM done / CRT done of pass 0
+    // optional phase marker of the caller (the engine records an event on the stream): 20 = a pass starts, 21 = its planes
+    // are written, 22 = its GEMM is launched, 23 = its CRT is launched
+    void (*mark)(void* ctx, int tag) = nullptr;
+    void* mark_ctx = nullptr;
     void release() {
         for (int i = 0; i < 2; i++) {
             if (planes[i]) cudaFree(planes[i]);
@@ -673,6 +678,7 @@ inline double i8_row_bound(int nmod, int kdim, unsigned __int128* Mout) {
 struct I8RunInfo {
     int nmod = 0, klen = 0, nsplit = 0, ntile = 0, passes = 0;
     double bits = 0;
+    double mma_ops = 0;  // 2 x int8 multiply-adds issued to the tensor cores (all moduli, whole padded tiles and k-blocks)
 };
 
 #define I8CK(call)                                                                                          \
@@ -786,6 +792,8 @@ inline int i8_kgemm_run(I8Plan& pl, I8EncodeFn enc, cudaStream_t st, int nsm, co
                 tiles.push_back(I8Tile{row0, col0, w, which});
             }
         }
+        pl.tile_area = 0;
+        for (auto& t : tiles) pl.tile_area += (double)I8_TM * t.ncols;
         if (pl.d_tiles) I8CK(cudaFree(pl.d_tiles));
         pl.d_tiles = nullptr;
         I8CK(cudaMalloc((void**)&pl.d_tiles, tiles.size() * sizeof(I8Tile)));
@@ -816,6 +824,7 @@ inline int i8_kgemm_run(I8Plan& pl, I8EncodeFn enc, cudaStream_t st, int nsm, co
         if ((rc = i8_grow(&pl.ws, &pl.ws_cap, nitems * I8_TILE_BYTES, err))) return rc;
         CUtensorMap amap, bmap[3];
         if (pl.prof[0] && passes == 0) cudaEventRecord(pl.prof[0], st);
+        if (pl.mark) pl.mark(pl.mark_ctx, 20);
         for (int op = 0; op < nop; op++) {
             const double* T = (op == 0 ? T1 : T2) + kb0;
             if ((rc = i8_grow(&pl.planes[op], &pl.planes_cap[op], plane_stride * nmod, err))) return rc;
@@ -825,6 +834,7 @@ inline int i8_kgemm_run(I8Plan& pl, I8EncodeFn enc, cudaStream_t st, int nsm, co
             pl.launches += 3;
         }
         if (pl.prof[1] && passes == 0) cudaEventRecord(pl.prof[1], st);
+        if (pl.mark) pl.mark(pl.mark_ctx, 21);
         const int8_t* pb = pl.planes[symmetric ? 0 : 1];
         if ((rc = i8_make_map(enc, &amap, pl.planes[0], (uint64_t)kk, (uint64_t)nbf, (uint64_t)nmod, ldk, plane_stride, I8_TM, err)))
             return rc;
@@ -846,6 +856,7 @@ inline int i8_kgemm_run(I8Plan& pl, I8EncodeFn enc, cudaStream_t st, int nsm, co
         i8_pipeline_kernel<I8KgemmTraits><<<(unsigned)std::min<size_t>(nitems, (size_t)nsm), I8_THREADS, i8_smem_bytes(), st>>>(amap, bmap[0], bmap[1],
                                                                                                             bmap[2], gp);
         if (pl.prof[2] && passes == 0) cudaEventRecord(pl.prof[2], st);
+        if (pl.mark) pl.mark(pl.mark_ctx, 22);
         I8CrtParams cp;
         cp.ntile = pl.ntile;
         cp.nsplit = nsplit;
@@ -863,11 +874,13 @@ inline int i8_kgemm_run(I8Plan& pl, I8EncodeFn enc, cudaStream_t st, int nsm, co
         cp.H_hi = (unsigned long long)((M / 2) >> 64);
         i8_crt(nmod, cp, st);
         if (pl.prof[3] && passes == 0) cudaEventRecord(pl.prof[3], st);
+        if (pl.mark) pl.mark(pl.mark_ctx, 23);
         pl.launches += 2;
         I8CK(cudaGetLastError());
         if (info) {
             info->nsplit = nsplit;
             info->bits = log2(Rb);
+            info->mma_ops += 2.0 * nmod * (double)ldk * pl.tile_area;
         }
     }
     if (info) {

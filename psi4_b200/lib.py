@@ -28,10 +28,17 @@ class Stats(ct.Structure):
         ("kgemm_flops", ct.c_double), ("launches", ct.c_uint64), ("hbm_tensor_bytes", ct.c_uint64),
         ("hbm_work_bytes", ct.c_uint64), ("n_shards", ct.c_int), ("q_begin", ct.c_int), ("q_end", ct.c_int),
         ("reduce_kind", ct.c_int), ("kgemm_kind", ct.c_int), ("kgemm_moduli", ct.c_int), ("half_kind", ct.c_int),
+        ("ms_half_i8", ct.c_double * 4), ("ms_kgemm_i8", ct.c_double * 3), ("half_i8_ops", ct.c_double),
+        ("half_i8_plane_bytes", ct.c_double), ("half_i8_convert_bytes", ct.c_double), ("kgemm_i8_ops", ct.c_double),
+        ("half_moduli", ct.c_int), ("half_i8_chunks", ct.c_int), ("half_i8_cached", ct.c_int), ("reserved_", ct.c_int),
     ]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        out = {}
+        for k, _ in self._fields_:
+            v = getattr(self, k)
+            out[k] = list(v) if hasattr(v, "__len__") else v
+        return out
 
 
 class B200JKError(RuntimeError):

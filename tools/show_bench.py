@@ -17,11 +17,19 @@ for f in sys.argv[1:]:
     def kern(ks, ind="   "):
         for k, v in ks.items():
             print(ind, k, {a: (round(b, 3) if isinstance(b, float) else b) for a, b in v.items() if not isinstance(b, (dict, str))})
+            for ph, pv in (v.get("int8_arm") or {}).items():
+                if isinstance(pv, dict):
+                    print(ind, "    i8", ph, {a: (round(b, 3) if isinstance(b, float) else b) for a, b in pv.items() if not isinstance(b, (dict, str))})
+                else:
+                    print(ind, "    i8", ph, pv)
 
     kern(d.get("kernels", {}))
     r = d.get("roofline")
     if r:
-        print(f"   roofline {r['achieved']:.2f} / {r['peak']:.2f} = {r['frac']:.3f}")
+        print(f"   roofline [{r.get('kernel', '')[:40]}] {r['achieved']:.2f} / {r['peak']:.2f} {r.get('unit')} = {r['frac']:.3f}")
+    r = d.get("roofline_fp64")
+    if r:
+        print(f"   roofline_fp64 {r['achieved']:.2f} / {r['peak']:.2f} = {r['frac']:.3f}")
     for k, v in d.get("workloads", {}).items():
         s2 = v["parity_spot"]
         print(f"   WL {k}: value {v['value_ms']:.2f} e2e {v['e2e_ms']:.2f} spot "
