@@ -437,6 +437,7 @@ struct FuseJ {
     int ldd;
     double* dpart;
     int dstride;
+    int gemm_col = 0;  // INT8 arm only: the sweep rides on the GEMM (one more column), not on the conversion (i8_half.cuh)
 };
 
 // orbital tiling of the half transform: nit tiles of iw columns (whole 8-column DMMA blocks), NB blocks per warp pair
@@ -717,6 +718,7 @@ int run_half_i8(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o
         f8.ldd = fj->ldd;
         f8.dpart = fj->dpart;
         f8.dstride = fj->dstride;
+        f8.gemm_col = fj->gemm_col;
     }
     const uint64_t l0 = s.i8h.launches;
     s.i8h.mark = i8_mark;
@@ -1128,12 +1130,21 @@ int run_device_K(b200jk* h, Shard& s, const Task& t, const double* const* dCl, c
             bool planes_stay = false;
             if (!wk && half_want_i8(h, s, o) && half_i8_arena(h, s, t.max_o, std::min(qc, s.nq), op, !one_T, &planes_stay) < 0)
                 planes_stay = false;
-            if (!wk && t.do_J && dD && dD[i] && can_fuse_j(o) && !planes_stay) {
+            // ... unless it can ride on the GEMM itself as one more column (exact in the integers: the same bits whether the
+            // planes were converted in this build or are cached); B200JK_I8_JCOL=0 keeps the separate first sweep
+            static int jcol = -1;
+            if (jcol < 0) {
+                const char* e = getenv("B200JK_I8_JCOL");
+                jcol = (e && e[0] == '0') ? 0 : 1;
+            }
+            const bool ride_gemm = planes_stay && jcol && i8h_can_fuse_col(s.i8h, o, half_i8_cluster());
+            if (!wk && t.do_J && dD && dD[i] && can_fuse_j(o) && (!planes_stay || ride_gemm)) {
                 const int ldd = round_up((int)N, 2);
                 fj_store.Dm = s.Dm + (size_t)i * N * ldd;
                 fj_store.ldd = ldd;
                 fj_store.dpart = s.dpart + (size_t)i * N * (size_t)s.nq;
                 fj_store.dstride = s.nq;
+                fj_store.gemm_col = ride_gemm ? 1 : 0;
                 fj = &fj_store;
                 PhaseScope ps(s, 0);
                 j_prep_dm_kernel<<<dim3((ldd + 127) / 128, (unsigned)N), 128, 0, s.stream>>>(dD[i], (int)N, ldd, t.lr ? 1 : 0,

@@ -19,6 +19,9 @@
 //     CRT       the bytes of all moduli -> the integer sum_k B' C' (floating-point CRT) -> * 2^-(eB + eC) -> T.
 // Exact except for the scaling of the two operands: |dT[m,q,i]| <~ 2^-bits |B_m[q,:]| |C[:,i]|.
 #pragma once
+#include <stdlib.h>
+#include <string.h>
+
 #include "i8_kgemm.cuh"
 
 namespace b2k {
@@ -62,6 +65,12 @@ __global__ void __launch_bounds__(256) i8h_rowscale_kernel(const double* __restr
 // First J sweep riding on the conversion (the converter reads every f64 row of the tensor anyway):
 //   dpart[m * dstride + q] = sum_k B_m[q,k] * Dm[m][n_k(m)]     (DGEMV 'N', dfhelper.cc:3193 / :3258; Dm as j_prep_dm_kernel
 // makes it), lane partials in k order, xor-shuffle tree: a fixed order.  Dm == nullptr: plain conversion.
+//
+// gemm_col = 1: the sweep rides on the GEMM instead -- the density row of row-block m, as residues, is gathered into the first
+// free column (index nocc) of the row-block's C^T tile, the GEMM computes it like any orbital, and i8h_dq_kernel rebuilds
+//   dpart[m][q] = sum_k B'_m[q,k] D'[m,n_k] * 2^-(eB(m,q) + eD(m))
+// from the residues: exact in the integers, so the same bits whether the planes were converted in this build or cached from
+// an earlier one (a sweep riding on the conversion cannot be used when the conversion is skipped).
 struct I8HalfFuseJ {
     const double* Dm;
     int ldd;
@@ -69,6 +78,7 @@ struct I8HalfFuseJ {
     int dstride;
     const int* cols;
     const size_t* cols_off;
+    int gemm_col;
 };
 
 // ---- residue planes of a chunk of row-blocks ------------------------------------------------------------------
@@ -196,6 +206,75 @@ __global__ void __launch_bounds__(128) i8h_gather_kernel(const int8_t* __restric
                     }
                 }
                 *reinterpret_cast<uint32_t*>(d + (size_t)j * cg_plane) = w;
+            }
+        }
+    }
+}
+
+// The same gather in 16-byte units (the default; B200JK_I8_GATHER=word keeps the word-wise kernel above for A/B).  The
+// word-wise kernel writes 4 bytes per store and took 3.0 ms per build whatever the shard size (1.9 TB/s): a fifth of the
+// whole build on the 592-row shard of the 8-GPU run.  Here one thread owns one 16-byte chunk (16 consecutive k) of one
+// orbital row: the kept-partner list of the row-block sits in shared memory, a chunk whose partners are consecutive
+// columns (first and last differ by 15: the list is sorted) is one unaligned 16-byte window of the rc row -- five aligned
+// words and four funnel shifts per modulus -- and a warp stores four whole 128-byte tile rows (512 contiguous bytes).
+// grid (nmc, ceil(opw / I8G_ROWS)), 256 threads, dynamic shared memory max_nkb * 128 ints.
+constexpr int I8G_ROWS = 16;
+__global__ void __launch_bounds__(256) i8h_gather16_kernel(const int8_t* __restrict__ rc, size_t rc_ld, size_t rc_plane, int o, int nmod,
+                                                           const int* __restrict__ sp, const int* __restrict__ kboff,
+                                                           const int* __restrict__ cols, const size_t* __restrict__ cols_off, int m0,
+                                                           int nit, int ntile_n, int8_t* __restrict__ cg, size_t cg_plane,
+                                                           const int8_t* __restrict__ rD, size_t rd_plane, int dcol) {
+    // rD / dcol: residue planes rD[j][m][n] of the density rows and the column (>= nocc) that carries row m of them in
+    // row-block m's tile (first J sweep as a column of the GEMM); dcol < 0: none
+    extern __shared__ int i8g_idx[];  // [nk * 128] kept partners of the row-block, -1 beyond sp(m)
+    const int m = m0 + blockIdx.x;
+    const int K = sp[m], nk = kboff[m + 1] - kboff[m];
+    const int* c = cols + cols_off[m];
+    for (int k = threadIdx.x; k < nk * I8_BK; k += 256) i8g_idx[k] = k < K ? __ldg(c + k) : -1;
+    __syncthreads();
+    const size_t blk = (size_t)ntile_n * I8_BK;
+    int8_t* base = cg + (size_t)(kboff[m] - kboff[m0]) * nit * blk;
+    const int i0 = blockIdx.y * I8G_ROWS, opw = nit * ntile_n;
+    const int nunit = nk * I8G_ROWS * 8;
+    for (int u = threadIdx.x; u < nunit; u += 256) {
+        const int ch = u & 7, rowi = (u >> 3) & (I8G_ROWS - 1), kb = u >> 7;  // I8G_ROWS * 8 = 128 units per k-block
+        const int i = i0 + rowi;
+        if (i >= opw) continue;
+        const int il = i / ntile_n, row = i - il * ntile_n;
+        const int* id = i8g_idx + kb * I8_BK + ch * 16;
+        const int n0 = id[0];
+        const bool run = n0 >= 0 && id[15] == n0 + 15;
+        int8_t* d = base + ((size_t)kb * nit + il) * blk + row * I8_BK + ((ch ^ (row & 7)) << 4);
+        const bool isd = i == dcol;
+        if ((i >= o && !isd) || n0 < 0) {  // a column beyond nocc, or a chunk wholly beyond sp(m) (the list ends in -1 padding)
+            for (int j = 0; j < nmod; j++) *reinterpret_cast<uint4*>(d + (size_t)j * cg_plane) = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+        }
+        const int8_t* srow = isd ? rD + (size_t)m * rc_ld : rc + (size_t)i * rc_ld;
+        const size_t rc_plane_i = isd ? rd_plane : rc_plane;
+        if (run) {
+            const int a = n0 & ~3, sh = (n0 & 3) * 8;
+            for (int j = 0; j < nmod; j++) {
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(srow + (size_t)j * rc_plane_i + a);
+                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = sh ? w[4] : 0u;
+                uint4 v;
+                v.x = __funnelshift_r(w0, w1, sh);
+                v.y = __funnelshift_r(w1, w2, sh);
+                v.z = __funnelshift_r(w2, w3, sh);
+                v.w = __funnelshift_r(w3, w4, sh);
+                *reinterpret_cast<uint4*>(d + (size_t)j * cg_plane) = v;
+            }
+        } else {
+            int n[16];
+#pragma unroll
+            for (int e = 0; e < 16; e++) n[e] = id[e];
+            for (int j = 0; j < nmod; j++) {
+                const int8_t* src = srow + (size_t)j * rc_plane_i;
+                uint32_t v[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int e = 0; e < 16; e++)
+                    if (n[e] >= 0) v[e >> 2] |= ((uint32_t)(uint8_t)src[n[e]]) << (8 * (e & 3));
+                *reinterpret_cast<uint4*>(d + (size_t)j * cg_plane) = make_uint4(v[0], v[1], v[2], v[3]);
             }
         }
     }
@@ -453,10 +532,38 @@ __global__ void __launch_bounds__(256) i8h_crt_kernel(const I8HalfCrtParams p) {
             int rr[NMOD];
 #pragma unroll
             for (int j = 0; j < NMOD; j++) rr[j] = (int)((w[j] >> (8 * c)) & 255u);
-            val = ldexp(i8_crt_value_fast<NMOD>(rr), -(eb + p.eC[i]));
+            // * 2^-(eB + eC): a power of two built from its exponent field is the same rounding as ldexp (one correctly
+            // rounded scaling) at a twentieth of its instructions; exponents outside the normal range take ldexp
+            const int e2 = -(eb + p.eC[i]);
+            const double f = i8_crt_value_fast<NMOD>(rr);
+            val = (e2 > -1000 && e2 < 1000) ? f * __hiloint2double((1023 + e2) << 20, 0) : ldexp(f, e2);
         }
         dst[c] = val;
     }
+}
+
+// First J sweep from the GEMM's extra column (I8HalfFuseJ::gemm_col): one thread per (row-block, q).
+struct I8HalfDqParams {
+    const uint8_t* ws;
+    size_t ws_mod_stride;
+    int opw, col, qc, qbeg, nq, m0, dstride;
+    const int *eB, *eD;
+    double* dpart;
+};
+template <int NMOD>
+__global__ void __launch_bounds__(256) i8h_dq_kernel(const I8HalfDqParams p) {
+    const int q = blockIdx.x * 256 + threadIdx.x;
+    if (q >= p.qc) return;
+    const int mloc = blockIdx.y, m = p.m0 + mloc;
+    const uint8_t* src = p.ws + ((size_t)mloc * p.qc + q) * p.opw + p.col;
+    int rr[NMOD];
+#pragma unroll
+    for (int j = 0; j < NMOD; j++) rr[j] = (int)src[(size_t)j * p.ws_mod_stride];
+    p.dpart[(size_t)m * p.dstride + p.qbeg + q] = ldexp(i8_crt_value_fast<NMOD>(rr), -(p.eB[(size_t)m * p.nq + p.qbeg + q] + p.eD[m]));
+}
+template <int NMOD>
+inline void i8h_launch_dq(const I8HalfDqParams& p, int nmc, cudaStream_t st) {
+    i8h_dq_kernel<NMOD><<<dim3((unsigned)((p.qc + 255) / 256), (unsigned)nmc), 256, 0, st>>>(p);
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------------------
@@ -477,6 +584,13 @@ struct I8HalfPlan {  // per shard
     size_t expoC_cap = 0;
     double* normpart = nullptr;
     size_t normpart_cap = 0;
+    // density rows of the first J sweep when it rides on the GEMM: residue planes rD[j][m][n], row scales
+    int8_t* rD = nullptr;
+    size_t rD_cap = 0;
+    int* expoD = nullptr;
+    size_t expoD_cap = 0;
+    double* normpartD = nullptr;
+    size_t normpartD_cap = 0;
     // scratch arena: planes | cg | ws
     uint8_t* arena = nullptr;
     size_t arena_cap = 0;
@@ -505,14 +619,17 @@ struct I8HalfPlan {  // per shard
             expoB[i] = nullptr;
             expo_valid[i] = false;
         }
-        void* ptrs[] = {d_kboff, rc, expoC, normpart};
+        void* ptrs[] = {d_kboff, rc, expoC, normpart, rD, expoD, normpartD};
         for (void* p : ptrs)
             if (p) cudaFree(p);
         d_kboff = nullptr;
         rc = nullptr;
         expoC = nullptr;
         normpart = nullptr;
-        rc_cap = expoC_cap = normpart_cap = 0;
+        rD = nullptr;
+        expoD = nullptr;
+        normpartD = nullptr;
+        rc_cap = expoC_cap = normpart_cap = rD_cap = expoD_cap = normpartD_cap = 0;
         kboff.clear();
     }
 };
@@ -627,6 +744,16 @@ inline void i8h_tiling(int o, int cluster, int* nit, int* ntile_n) {
     *ntile_n = ((opw0 + *nit - 1) / *nit + ngran - 1) / ngran * ngran;
 }
 
+// The first J sweep can ride on the GEMM when the tiling has a free column behind the nocc orbitals and the 16-byte gather
+// (which knows about the density column) can run
+inline bool i8h_can_fuse_col(const I8HalfPlan& pl, int o, int cluster) {
+    if (cluster != 2 && cluster != 4) cluster = 1;
+    int nit, ntile_n;
+    i8h_tiling(o, cluster, &nit, &ntile_n);
+    const char* e = getenv("B200JK_I8_GATHER");
+    return o > 0 && o < nit * ntile_n && !(e && !strcmp(e, "word")) && (size_t)pl.max_nkb_row * I8_BK * sizeof(int) <= 48 * 1024;
+}
+
 // bytes of arena one row-block with nkb k-blocks needs
 inline size_t i8h_cost(int nmod, int nkb, int nqt, int qc, int nit, int ntile_n) {
     return (size_t)nmod * ((size_t)nkb * ((size_t)nqt * I8H_TILE + (size_t)nit * ntile_n * I8_BK) + (size_t)qc * nit * ntile_n);
@@ -693,6 +820,22 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
     i8_rowscale_kernel<<<(o + 127) / 128, 128, 0, st>>>(pl.normpart, nchunkn, o, Rb, pl.expoC);
     i8_convert(nmod, Ct, (size_t)ldc, nbf, o, pl.expoC, pl.rc, rc_ld, rc_plane, st);
     pl.launches += 3;
+    // density rows of a first J sweep that rides on the GEMM: the same row kernels on the rows of D'
+    const bool fuse_col = fuse && fuse->gemm_col;
+    const size_t rd_plane = rc_ld * (size_t)nbf;
+    if (fuse_col) {
+        if (!i8h_can_fuse_col(pl, o, cluster)) {
+            if (err) *err = "the first J sweep cannot ride on the GEMM: no free column behind nocc";
+            return 2;
+        }
+        if ((rc = i8_grow(&pl.rD, &pl.rD_cap, rd_plane * nmod, err))) return rc;
+        if ((rc = i8_grow(&pl.expoD, &pl.expoD_cap, (size_t)nbf, err))) return rc;
+        if ((rc = i8_grow(&pl.normpartD, &pl.normpartD_cap, (size_t)nbf * nchunkn, err))) return rc;
+        i8_rownorm_kernel<<<dim3(nchunkn, nbf), 256, 0, st>>>(fuse->Dm, (size_t)fuse->ldd, nbf, nchunkn, pl.normpartD);
+        i8_rowscale_kernel<<<(nbf + 127) / 128, 128, 0, st>>>(pl.normpartD, nchunkn, nbf, Rb, pl.expoD);
+        i8_convert(nmod, fuse->Dm, (size_t)fuse->ldd, nbf, nbf, pl.expoD, pl.rD, rc_ld, rd_plane, st);
+        pl.launches += 3;
+    }
 
     int nit, ntile_n, nit_p, ntile_p;
     i8h_tiling(o, cluster, &nit, &ntile_n);
@@ -748,7 +891,7 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
         return 3;
     }
     const bool cached = chunks.size() == 1 && i8h_cached(pl, which, qbeg, qc, nmod);
-    if (cached && fuse) {
+    if (cached && fuse && !fuse_col) {
         if (err) *err = "the first J sweep cannot ride on a conversion that is skipped (planes cached)";
         return 2;
     }
@@ -761,7 +904,7 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
         if (pl.mark) pl.mark(pl.mark_ctx, 10);
         if (cached) pl.conversions_skipped++;
         I8HalfFuseJ fjv = {nullptr, 0, nullptr, 0, nullptr, nullptr};
-        if (fuse) {
+        if (fuse && !fuse_col) {
             fjv = *fuse;
             fjv.cols = d_cols;
             fjv.cols_off = d_cols_off;
@@ -771,8 +914,19 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
                          planes, plane_stride, fjv, pl.max_nkb_row, st);
         if (prof) cudaEventRecord(pl.prof[1], st);
         if (pl.mark) pl.mark(pl.mark_ctx, 11);
-        i8h_gather_kernel<<<dim3((unsigned)nmc, (unsigned)((opw + 3) / 4)), 128, 0, st>>>(pl.rc, rc_ld, rc_plane, o, nmod, d_sp, pl.d_kboff, d_cols,
-                                                                                        d_cols_off, c.m0, nit, ntile_n, cg, cg_plane);
+        static int gather_word = -1;
+        if (gather_word < 0) {
+            const char* e = getenv("B200JK_I8_GATHER");
+            gather_word = (e && !strcmp(e, "word")) ? 1 : 0;
+        }
+        if (!fuse_col && (gather_word || (size_t)pl.max_nkb_row * I8_BK * sizeof(int) > 48 * 1024))
+            i8h_gather_kernel<<<dim3((unsigned)nmc, (unsigned)((opw + 3) / 4)), 128, 0, st>>>(pl.rc, rc_ld, rc_plane, o, nmod, d_sp, pl.d_kboff,
+                                                                                            d_cols, d_cols_off, c.m0, nit, ntile_n, cg, cg_plane);
+        else
+            i8h_gather16_kernel<<<dim3((unsigned)nmc, (unsigned)((opw + I8G_ROWS - 1) / I8G_ROWS)), 256,
+                                  (size_t)pl.max_nkb_row * I8_BK * sizeof(int), st>>>(pl.rc, rc_ld, rc_plane, o, nmod, d_sp, pl.d_kboff, d_cols,
+                                                                                      d_cols_off, c.m0, nit, ntile_n, cg, cg_plane,
+                                                                                      fuse_col ? pl.rD : nullptr, rd_plane, fuse_col ? o : -1);
         if (prof) cudaEventRecord(pl.prof[2], st);
         if (pl.mark) pl.mark(pl.mark_ctx, 12);
         I8HalfParams gp;
@@ -815,6 +969,23 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
         cp.H_lo = (unsigned long long)(M / 2);
         cp.H_hi = (unsigned long long)((M / 2) >> 64);
         I8H_DISPATCH(nmod, i8h_launch_crt, cp, nmc, st);
+        if (fuse_col) {
+            I8HalfDqParams dp;
+            dp.ws = ws;
+            dp.ws_mod_stride = gp.ws_mod_stride;
+            dp.opw = opw;
+            dp.col = o;
+            dp.qc = qc;
+            dp.qbeg = qbeg;
+            dp.nq = nq;
+            dp.m0 = c.m0;
+            dp.dstride = fuse->dstride;
+            dp.eB = pl.expoB[which];
+            dp.eD = pl.expoD;
+            dp.dpart = fuse->dpart;
+            I8H_DISPATCH(nmod, i8h_launch_dq, dp, nmc, st);
+            pl.launches++;
+        }
         if (prof) cudaEventRecord(pl.prof[4], st);
         if (pl.mark) pl.mark(pl.mark_ctx, 14);
         pl.launches += 4;

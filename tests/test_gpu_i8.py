@@ -265,3 +265,39 @@ def test_i8_half_golden_vectors():
             assert np.abs(wK[i] - g[f"wK_{tag}{i}"]).max() < TOL
             assert np.abs(J[i] - g[f"J_{tag}{i}"]).max() < TOL
     e.close()
+
+
+def test_i8_first_j_sweep_rides_on_the_gemm(oracle):
+    """When the residue planes of the shard stay resident, the first J sweep d_Q = B_Q . D (DGEMV 'N', dfhelper.cc:3193 /
+    :3258) is one more column of the residue GEMM (I8HalfFuseJ::gemm_col): exact in the integers, so the build that
+    converts the planes and the builds that find them cached give the same bits, for RHF-like and for general densities,
+    and the tensor is read once less (j_bytes counts one pass, the second sweep)."""
+    rng = np.random.default_rng(77)
+    n, a = 300, 200
+    keep = random_mask(rng, n, 0.5)
+    sp, d, B, P = make(oracle, rng, n, a, keep, 0.1)
+    noccs = [23, 40]
+    Cl = [np.linalg.qr(rng.standard_normal((n, o)))[0] for o in noccs]
+    D = [2.0 * c @ c.T for c in Cl]
+    Jo, Ko, _, _ = oracle.build_JK(sp, P, Cl, None, D=D)
+    e = engine_for(d, P, n, a, "i8")
+    e.set_half("i8")
+    J1, K1, _ = e.compute(Cl, None, D)
+    st = e.stats()
+    assert st["half_kind"] == 1 and st["half_i8_cached"] == len(noccs) - 1, st  # the second density finds the planes of the first
+    check(J1, Jo, what="J (first build)")
+    check(K1, Ko, what="K")
+    ptri = sum(int(np.count_nonzero(keep[m, m:])) for m in range(n))
+    assert st["j_bytes"] == 8.0 * a * ptri, (st["j_bytes"], 8.0 * a * ptri)  # one pass: the batched second sweep
+    J2, K2, _ = e.compute(Cl, None, D)
+    assert e.stats()["half_i8_cached"] == len(noccs)
+    for x, y in zip(J1 + K1, J2 + K2):
+        assert np.array_equal(x, y)
+    # a general (non-symmetric) density pair through the same column
+    Cr = [np.linalg.qr(rng.standard_normal((n, o)))[0] for o in noccs]
+    Dg = [x @ y.T for x, y in zip(Cl, Cr)]
+    Jo, Ko, _, _ = oracle.build_JK(sp, P, Cl, Cr, D=Dg)
+    J, K, _ = e.compute(Cl, Cr, Dg)
+    check(J, Jo, what="J general")
+    check(K, Ko, what="K general")
+    e.close()
