@@ -510,6 +510,7 @@ def i8_table(res, hbm_peak):
         t_bytes = 8.0 * cfg["nbf"] * (st["q_end"] - st["q_begin"]) * (cfg["nocc"] + cfg["nocc"] % 2) * cfg["nmat"] * (1 if res["Crl"] is None else 2)
         out["half_transform"] = {
             "moduli": st["half_moduli"], "chunks": st["half_i8_chunks"], "planes_cached": st["half_i8_cached"],
+            "resident_row_blocks": st["half_i8_resident_rows"],
             "convert": {"ms": cv, "bound": "hbm", "bytes": st["half_i8_convert_bytes"],
                         "gbs": st["half_i8_convert_bytes"] / (cv * 1e-3) / 1e9 if cv else 0.0,
                         "frac_of_hbm_peak": st["half_i8_convert_bytes"] / (cv * 1e-3) / 1e9 / hbm_peak if cv else None,

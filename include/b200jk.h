@@ -218,7 +218,7 @@ typedef struct {
     int half_moduli;       /* moduli of the half transform's residue arm (12: 47 bits below |B row| |C column|)      */
     int half_i8_chunks;    /* row-block chunks the scratch arena forced (summed over transforms)                     */
     int half_i8_cached;    /* transforms that found their residue planes cached from an earlier build                */
-    int reserved_;
+    int half_i8_resident_rows; /* row-blocks [0, n) whose residue planes stay in HBM across builds (nbf: all of them)  */
 } b200jk_stats;
 
 int b200jk_get_stats(const b200jk_t* h, b200jk_stats* out);

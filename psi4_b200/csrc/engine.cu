@@ -168,7 +168,7 @@ struct Shard {
     // sub-phases of the INT8 arms of the current build: (tag, event) in stream order (tags: i8_half.cuh / i8_kgemm.cuh `mark`)
     std::vector<std::pair<int, cudaEvent_t>> marks;
     double i8h_ops = 0, i8h_plane_bytes = 0, i8h_convert_bytes = 0, i8k_ops = 0;
-    int i8h_nmod = 0, i8h_chunks = 0, i8h_cached = 0;
+    int i8h_nmod = 0, i8h_chunks = 0, i8h_cached = 0, i8h_resident_rows = 0;
 };
 }  // namespace
 
@@ -688,7 +688,13 @@ int half_i8_arena(b200jk* h, Shard& s, int max_o, int qc, int op, bool two_opera
             k4 = (size_t)kgemm_moduli(h) * nbf * ((size_t)qc * op + 128) * (two_operands ? 2 : 1) + ((size_t)4 << 30);
         const size_t reserve = (size_t)4 << 30;
         if (avail < k4 + reserve + mn) return -1;
-        const size_t want = std::min(all, avail - k4 - reserve);
+        size_t want = std::min(all, avail - k4 - reserve);
+        static long cap_mb = -1;  // B200JK_I8_ARENA_MB: upper bound of the arena (tests of the partly resident plan)
+        if (cap_mb < 0) {
+            const char* e = getenv("B200JK_I8_ARENA_MB");
+            cap_mb = e ? atol(e) : 0;
+        }
+        if (cap_mb > 0) want = std::max(mn, std::min(want, (size_t)cap_mb << 20));
         if (want > s.i8h.arena_cap) {
             s.i8h.release_arena();
             if (cudaMalloc((void**)&s.i8h.arena, want) != cudaSuccess) {
@@ -735,6 +741,7 @@ int run_half_i8(b200jk* h, Shard& s, int which, const double* Ct, int ldc, int o
     s.i8h_nmod = info.nmod;
     s.i8h_chunks += info.nchunks;
     s.i8h_cached += info.cached;
+    s.i8h_resident_rows = info.resident_rows;
     return 0;
 }
 
@@ -1137,8 +1144,17 @@ int run_device_K(b200jk* h, Shard& s, const Task& t, const double* const* dCl, c
                 const char* e = getenv("B200JK_I8_JCOL");
                 jcol = (e && e[0] == '0') ? 0 : 1;
             }
-            const bool ride_gemm = planes_stay && jcol && i8h_can_fuse_col(s.i8h, o, half_i8_cluster());
-            if (!wk && t.do_J && dD && dD[i] && can_fuse_j(o) && (!planes_stay || ride_gemm)) {
+            const bool i8_arm = !wk && half_want_i8(h, s, o) && s.i8h.arena;
+            const bool ride_gemm = i8_arm && jcol && i8h_can_fuse_col(s.i8h, o, half_i8_cluster());
+            // (part of the planes stays resident even when not all of them fit, unless B200JK_I8_RESIDENT=0: riding on the
+            // conversion is then the A/B arm only)
+            static int resident = -1;
+            if (resident < 0) {
+                const char* e = getenv("B200JK_I8_RESIDENT");
+                resident = (e && e[0] == '0') ? 0 : 1;
+            }
+            const bool ride_convert = !i8_arm || (!planes_stay && !resident);
+            if (!wk && t.do_J && dD && dD[i] && can_fuse_j(o) && (ride_gemm || ride_convert)) {
                 const int ldd = round_up((int)N, 2);
                 fj_store.Dm = s.Dm + (size_t)i * N * ldd;
                 fj_store.ldd = ldd;
@@ -1224,7 +1240,7 @@ int collect_stats(b200jk* h) {
     for (int i = 0; i < 4; i++) st.ms_half_i8[i] = 0;
     for (int i = 0; i < 3; i++) st.ms_kgemm_i8[i] = 0;
     st.half_i8_ops = st.half_i8_plane_bytes = st.half_i8_convert_bytes = st.kgemm_i8_ops = 0;
-    st.half_moduli = st.half_i8_chunks = st.half_i8_cached = 0;
+    st.half_moduli = st.half_i8_chunks = st.half_i8_cached = st.half_i8_resident_rows = 0;
     for (auto& s : h->sh) {
         // sub-phases of the INT8 arms: the time between two consecutive marks belongs to the later one's tag
         double sub_h[4] = {0, 0, 0, 0}, sub_k[3] = {0, 0, 0};
@@ -1245,6 +1261,7 @@ int collect_stats(b200jk* h) {
         st.half_moduli = std::max(st.half_moduli, s.i8h_nmod);
         st.half_i8_chunks += s.i8h_chunks;
         st.half_i8_cached += s.i8h_cached;
+        st.half_i8_resident_rows = std::max(st.half_i8_resident_rows, s.i8h_resident_rows);
         double acc[7] = {0, 0, 0, 0, 0, 0, 0};
         for (auto& ph : s.phases) {
             float ms = 0;
@@ -1360,7 +1377,7 @@ void begin_compute(b200jk* h) {
         s.evused = 0;
         s.launches = 0;
         s.i8h_ops = s.i8h_plane_bytes = s.i8h_convert_bytes = s.i8k_ops = 0;
-        s.i8h_nmod = s.i8h_chunks = s.i8h_cached = 0;
+        s.i8h_nmod = s.i8h_chunks = s.i8h_cached = s.i8h_resident_rows = 0;
     }
 }
 

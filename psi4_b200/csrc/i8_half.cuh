@@ -211,70 +211,96 @@ __global__ void __launch_bounds__(128) i8h_gather_kernel(const int8_t* __restric
     }
 }
 
-// The same gather in 16-byte units (the default; B200JK_I8_GATHER=word keeps the word-wise kernel above for A/B).  The
-// word-wise kernel writes 4 bytes per store and took 3.0 ms per build whatever the shard size (1.9 TB/s): a fifth of the
-// whole build on the 592-row shard of the 8-GPU run.  Here one thread owns one 16-byte chunk (16 consecutive k) of one
-// orbital row: the kept-partner list of the row-block sits in shared memory, a chunk whose partners are consecutive
-// columns (first and last differ by 15: the list is sorted) is one unaligned 16-byte window of the rc row -- five aligned
-// words and four funnel shifts per modulus -- and a warp stores four whole 128-byte tile rows (512 contiguous bytes).
-// grid (nmc, ceil(opw / I8G_ROWS)), 256 threads, dynamic shared memory max_nkb * 128 ints.
+// The same gather in 16-byte units through shared memory (the default; B200JK_I8_GATHER=word keeps the word-wise kernel
+// above for A/B).  The word-wise kernel took 3.0 ms per build whatever the shard size (1.9 TB/s of stores): a fifth of the
+// whole build on the 592-row shard of the 8-GPU run, and ncu shows it waiting on its own loads (long-scoreboard stalls,
+// 26 % issue-active): every 4 output bytes cost two dependent L2 accesses.  Here a CTA takes 16 orbital rows of one
+// row-block; per modulus it stages those 16 rows of the residue plane (16 x nbf bytes, L2-resident source) in shared
+// memory with coalesced 16-byte loads, and one thread then owns one 16-byte chunk (16 consecutive k) of one orbital row:
+// a chunk whose partners are consecutive columns (first and last differ by 15: the list is sorted) is one unaligned
+// 16-byte window of the staged row -- five shared-memory words and four funnel shifts -- and a warp stores four whole
+// 128-byte tile rows (512 contiguous bytes).  The row pitch is 9 words modulo 32, which spreads the 4 rows x 8 chunks a
+// warp reads at a time over all 32 banks.
+// grid (nmc, ceil(opw / I8G_ROWS)), 256 threads, dynamic shared memory i8g_smem_bytes().
 constexpr int I8G_ROWS = 16;
+__host__ __device__ inline size_t i8g_pitch_words(size_t rc_ld) { return rc_ld / 4 + 8 + 1; }  // >= 16 bytes of over-read room; = 9 (mod 32) as rc_ld % 128 == 0
+inline size_t i8g_smem_bytes(int max_nkb, size_t rc_ld) {
+    return (size_t)max_nkb * I8_BK * sizeof(int) + (size_t)I8G_ROWS * i8g_pitch_words(rc_ld) * 4;
+}
 __global__ void __launch_bounds__(256) i8h_gather16_kernel(const int8_t* __restrict__ rc, size_t rc_ld, size_t rc_plane, int o, int nmod,
                                                            const int* __restrict__ sp, const int* __restrict__ kboff,
                                                            const int* __restrict__ cols, const size_t* __restrict__ cols_off, int m0,
                                                            int nit, int ntile_n, int8_t* __restrict__ cg, size_t cg_plane,
-                                                           const int8_t* __restrict__ rD, size_t rd_plane, int dcol) {
+                                                           const int8_t* __restrict__ rD, size_t rd_plane, int dcol, int max_nkb) {
     // rD / dcol: residue planes rD[j][m][n] of the density rows and the column (>= nocc) that carries row m of them in
     // row-block m's tile (first J sweep as a column of the GEMM); dcol < 0: none
-    extern __shared__ int i8g_idx[];  // [nk * 128] kept partners of the row-block, -1 beyond sp(m)
+    extern __shared__ int i8g_idx[];  // [max_nkb * 128] kept partners of the row-block, -1 beyond sp(m); then the staged rows
+    const int pitchw = (int)i8g_pitch_words(rc_ld);
+    uint32_t* rows = reinterpret_cast<uint32_t*>(i8g_idx + (size_t)max_nkb * I8_BK);  // [I8G_ROWS][pitchw]
     const int m = m0 + blockIdx.x;
     const int K = sp[m], nk = kboff[m + 1] - kboff[m];
     const int* c = cols + cols_off[m];
     for (int k = threadIdx.x; k < nk * I8_BK; k += 256) i8g_idx[k] = k < K ? __ldg(c + k) : -1;
-    __syncthreads();
     const size_t blk = (size_t)ntile_n * I8_BK;
     int8_t* base = cg + (size_t)(kboff[m] - kboff[m0]) * nit * blk;
     const int i0 = blockIdx.y * I8G_ROWS, opw = nit * ntile_n;
     const int nunit = nk * I8G_ROWS * 8;
-    for (int u = threadIdx.x; u < nunit; u += 256) {
-        const int ch = u & 7, rowi = (u >> 3) & (I8G_ROWS - 1), kb = u >> 7;  // I8G_ROWS * 8 = 128 units per k-block
-        const int i = i0 + rowi;
-        if (i >= opw) continue;
-        const int il = i / ntile_n, row = i - il * ntile_n;
-        const int* id = i8g_idx + kb * I8_BK + ch * 16;
-        const int n0 = id[0];
-        const bool run = n0 >= 0 && id[15] == n0 + 15;
-        int8_t* d = base + ((size_t)kb * nit + il) * blk + row * I8_BK + ((ch ^ (row & 7)) << 4);
-        const bool isd = i == dcol;
-        if ((i >= o && !isd) || n0 < 0) {  // a column beyond nocc, or a chunk wholly beyond sp(m) (the list ends in -1 padding)
-            for (int j = 0; j < nmod; j++) *reinterpret_cast<uint4*>(d + (size_t)j * cg_plane) = make_uint4(0u, 0u, 0u, 0u);
-            continue;
+    const int vec_per_row = (int)(rc_ld / 16);
+    for (int j = 0; j < nmod; j++) {
+        __syncthreads();  // the list is written (j = 0) / the rows of the previous modulus have been read
+        for (int v = threadIdx.x; v < I8G_ROWS * vec_per_row; v += 256) {
+            const int rr = v / vec_per_row, x = v - rr * vec_per_row;
+            const int i = i0 + rr;
+            const int8_t* src = nullptr;
+            if (i < o)
+                src = rc + (size_t)j * rc_plane + (size_t)i * rc_ld;
+            else if (i == dcol)
+                src = rD + (size_t)j * rd_plane + (size_t)m * rc_ld;
+            if (src) {
+                const uint4 q = *reinterpret_cast<const uint4*>(src + (size_t)x * 16);
+                uint32_t* dst = rows + rr * pitchw + x * 4;
+                // the four words go out rotated by the lane's octet: lanes l, l+8, l+16, l+24 (same bank otherwise) hit four banks
+                const int rot = (threadIdx.x >> 3) & 3;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int w = (rot + t) & 3;
+                    dst[w] = w == 0 ? q.x : (w == 1 ? q.y : (w == 2 ? q.z : q.w));
+                }
+            }
         }
-        const int8_t* srow = isd ? rD + (size_t)m * rc_ld : rc + (size_t)i * rc_ld;
-        const size_t rc_plane_i = isd ? rd_plane : rc_plane;
-        if (run) {
-            const int a = n0 & ~3, sh = (n0 & 3) * 8;
-            for (int j = 0; j < nmod; j++) {
-                const uint32_t* w = reinterpret_cast<const uint32_t*>(srow + (size_t)j * rc_plane_i + a);
-                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = sh ? w[4] : 0u;
+        __syncthreads();
+        for (int u = threadIdx.x; u < nunit; u += 256) {
+            const int ch = u & 7, rowi = (u >> 3) & (I8G_ROWS - 1), kb = u >> 7;  // I8G_ROWS * 8 = 128 units per k-block
+            const int i = i0 + rowi;
+            if (i >= opw) continue;
+            const int il = i / ntile_n, row = i - il * ntile_n;
+            const int* id = i8g_idx + kb * I8_BK + ch * 16;
+            const int n0 = id[0];
+            uint4* d = reinterpret_cast<uint4*>(base + ((size_t)kb * nit + il) * blk + row * I8_BK + ((ch ^ (row & 7)) << 4) + (size_t)j * cg_plane);
+            if ((i >= o && i != dcol) || n0 < 0) {  // a column beyond nocc, or a chunk wholly beyond sp(m) (the list ends in -1 padding)
+                *d = make_uint4(0u, 0u, 0u, 0u);
+                continue;
+            }
+            const uint32_t* srow = rows + rowi * pitchw;
+            if (id[15] == n0 + 15) {
+                const int sh = (n0 & 3) * 8;
+                const uint32_t* w = srow + (n0 >> 2);
+                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];  // w[4]: inside the padded row
                 uint4 v;
                 v.x = __funnelshift_r(w0, w1, sh);
                 v.y = __funnelshift_r(w1, w2, sh);
                 v.z = __funnelshift_r(w2, w3, sh);
                 v.w = __funnelshift_r(w3, w4, sh);
-                *reinterpret_cast<uint4*>(d + (size_t)j * cg_plane) = v;
-            }
-        } else {
-            int n[16];
-#pragma unroll
-            for (int e = 0; e < 16; e++) n[e] = id[e];
-            for (int j = 0; j < nmod; j++) {
-                const int8_t* src = srow + (size_t)j * rc_plane_i;
+                *d = v;
+            } else {
+                const uint8_t* sb = reinterpret_cast<const uint8_t*>(srow);
                 uint32_t v[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-                for (int e = 0; e < 16; e++)
-                    if (n[e] >= 0) v[e >> 2] |= ((uint32_t)(uint8_t)src[n[e]]) << (8 * (e & 3));
-                *reinterpret_cast<uint4*>(d + (size_t)j * cg_plane) = make_uint4(v[0], v[1], v[2], v[3]);
+                for (int e = 0; e < 16; e++) {
+                    const int n = id[e];
+                    if (n >= 0) v[e >> 2] |= ((uint32_t)sb[n]) << (8 * (e & 3));
+                }
+                *d = make_uint4(v[0], v[1], v[2], v[3]);
             }
         }
     }
@@ -572,6 +598,7 @@ struct I8HalfPlan {  // per shard
     std::vector<int> kboff;  // [nbf + 1]
     int max_nkb_row = 0;     // largest nkb(m)
     double sum_sp = 0;       // kept pairs (sum of sp(m))
+    std::vector<double> sp_prefix;  // [nbf + 1] running sum of sp(m)
     int* d_kboff = nullptr;
     // scales of the tensor rows, per tensor; valid until the tensor changes
     int* expoB[3] = {nullptr, nullptr, nullptr};
@@ -599,7 +626,7 @@ struct I8HalfPlan {  // per shard
     int crt_nmod = 0;  // moduli the constants of the floating-point CRT were uploaded for
     // When the arena holds the planes of the whole Q range in one chunk they stay valid until the tensor changes: the next
     // build (and the second density of an open-shell build) skips the conversion -- which is most of the arm's time.
-    int cache_which = -1, cache_qbeg = -1, cache_qc = -1, cache_nmod = -1;
+    int cache_which = -1, cache_qbeg = -1, cache_qc = -1, cache_nmod = -1, cache_mr = -1;
     uint64_t conversions_skipped = 0;
     cudaEvent_t prof[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // optional: start / convert / gather / GEMM / CRT of chunk 0
     // optional phase marker of the caller (the engine records an event on the stream): 10 = a chunk starts, 11 / 12 / 13 / 14 =
@@ -640,8 +667,10 @@ inline int i8h_set_layout(I8HalfPlan& pl, const std::vector<int>& sp, std::strin
     pl.kboff[0] = 0;
     pl.max_nkb_row = 0;
     pl.sum_sp = 0;
+    pl.sp_prefix.assign(nbf + 1, 0.0);
     for (size_t m = 0; m < nbf; m++) {
         pl.sum_sp += (double)sp[m];
+        pl.sp_prefix[m + 1] = pl.sp_prefix[m] + (double)sp[m];
         pl.kboff[m + 1] = pl.kboff[m] + (sp[m] + I8_BK - 1) / I8_BK;
         pl.max_nkb_row = std::max(pl.max_nkb_row, pl.kboff[m + 1] - pl.kboff[m]);
     }
@@ -734,6 +763,8 @@ struct I8HalfInfo {
     // work of this call: 2 x int8 multiply-adds issued to the tensor cores (all moduli, whole padded tiles), bytes of residue
     // planes the GEMM read, bytes the conversions that RAN moved (f64 rows read + planes written)
     double mma_ops = 0, plane_bytes = 0, convert_bytes = 0;
+    int resident_rows = 0;  // row-blocks [0, resident_rows) keep their planes across builds
+    int resident_hit = 0;   // ... and this call found them valid (their conversion was skipped)
 };
 
 // orbital tiling: nit tiles of ntile_n columns (whole 8-row swizzle atoms per cluster slice), opw = nit * ntile_n >= o
@@ -751,7 +782,8 @@ inline bool i8h_can_fuse_col(const I8HalfPlan& pl, int o, int cluster) {
     int nit, ntile_n;
     i8h_tiling(o, cluster, &nit, &ntile_n);
     const char* e = getenv("B200JK_I8_GATHER");
-    return o > 0 && o < nit * ntile_n && !(e && !strcmp(e, "word")) && (size_t)pl.max_nkb_row * I8_BK * sizeof(int) <= 48 * 1024;
+    const size_t rc_ld = (pl.kboff.size() - 1 + 127) / 128 * 128;
+    return o > 0 && o < nit * ntile_n && !(e && !strcmp(e, "word")) && i8g_smem_bytes(pl.max_nkb_row, rc_ld) <= 48 * 1024;
 }
 
 // bytes of arena one row-block with nkb k-blocks needs
@@ -770,8 +802,8 @@ inline void i8h_arena_need(const I8HalfPlan& pl, int nmod, int qc, int max_o, in
         mx = std::max(mx, c);
         all += c;
     }
-    *min_bytes = mx + 65536;
-    *all_bytes = all + 65536;
+    *min_bytes = 2 * mx + 2 * 65536 + 2048;  // i8_half_run keeps a work region of two row-blocks' worth at least
+    *all_bytes = all + 65536 + 2048;
 }
 
 // T[m][q][i] (pitch Tpitch per m, op per q) for q in [qbeg, qbeg + qc) of tensor `which`.
@@ -842,76 +874,119 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
     i8h_tiling(max_o, cluster, &nit_p, &ntile_p);  // the plan is made for the largest nocc
     const int opw = nit * ntile_n;
     const int nqt = (qc + I8_TM - 1) / I8_TM;
-    struct Chunk {
-        int m0, m1;
-        size_t nkb;
-    };
-    std::vector<Chunk> chunks;
-    size_t max_nkb = 0, max_nm = 0;
-    // the three regions are carved at the maxima over the chunks (planes and C^T by k-blocks, residues by row-blocks), which
-    // different chunks may attain: plan against a budget and shrink it until the carve fits
-    for (size_t budget = pl.arena_cap;; budget -= budget / 16) {
-        chunks.clear();
-        max_nkb = max_nm = 0;
-        const size_t slack = 65536;
-        int m0 = 0;
-        size_t nkb = 0, cost = slack;
-        for (int m = 0; m < nbf; m++) {
-            const int nk = pl.kboff[m + 1] - pl.kboff[m];
-            const size_t c = std::max(i8h_cost(nmod, nk, nqt, qc, nit_p, ntile_p), i8h_cost(nmod, nk, nqt, qc, nit, ntile_n));
-            if (m > m0 && cost + c > budget) {
-                chunks.push_back(Chunk{m0, m, nkb});
-                m0 = m;
-                nkb = 0;
-                cost = slack;
-            }
-            nkb += (size_t)nk;
-            cost += c;
-            if (cost > budget) {
-                if (err) *err = "scratch arena too small for one row-block of residue planes";
-                return 3;
-            }
-        }
-        chunks.push_back(Chunk{m0, nbf, nkb});
-        for (auto& c : chunks) {
-            max_nkb = std::max(max_nkb, c.nkb);
-            max_nm = std::max(max_nm, (size_t)(c.m1 - c.m0));
-        }
-        const size_t carve = (size_t)nmod * (max_nkb * ((size_t)nqt * I8H_TILE + (size_t)nit * ntile_n * I8_BK) + max_nm * (size_t)qc * opw);
-        if (carve <= pl.arena_cap) break;
+    // ---- plan: resident planes + work region ------------------------------------------------------------------------
+    // The arena is split into a RESIDENT region -- the residue planes of row-blocks [0, m_r), which stay valid until the
+    // tensor changes, so that later builds (and the second density of an open-shell build) skip their conversion -- and
+    // a WORK region that holds, chunk by chunk, the gathered C^T and the residues of the GEMM (and, for the row-blocks
+    // behind m_r, their planes, converted in every build).  Everything fits: m_r = nbf, one chunk.  Otherwise a fifth of
+    // the arena is work region and the rest resident: C60 on one GPU keeps a third of its 132 GB of planes.
+    // B200JK_I8_RESIDENT=0: nothing resident unless everything fits (the round-2 rule, for A/B).
+    static int resident_env = -1;
+    if (resident_env < 0) {
+        const char* e = getenv("B200JK_I8_RESIDENT");
+        resident_env = (e && e[0] == '0') ? 0 : 1;
     }
-    const size_t plane_stride = max_nkb * (size_t)nqt * I8H_TILE;
-    const size_t cg_plane = max_nkb * (size_t)nit * ntile_n * I8_BK;
-    int8_t* planes = reinterpret_cast<int8_t*>(pl.arena);
-    int8_t* cg = planes + plane_stride * nmod;
-    uint8_t* ws = reinterpret_cast<uint8_t*>(cg + cg_plane * nmod);
-    const size_t ws_bytes = (size_t)nmod * max_nm * qc * opw;
-    if ((size_t)(ws - pl.arena) + ws_bytes > pl.arena_cap) {
-        if (err) *err = "scratch arena accounting";
+    const size_t align = 1024, slack = 65536;
+    auto planes_of = [&](int m) { return (size_t)nmod * (size_t)(pl.kboff[m + 1] - pl.kboff[m]) * (size_t)nqt * I8H_TILE; };
+    auto cgws_of = [&](int m) {
+        const size_t nk = (size_t)(pl.kboff[m + 1] - pl.kboff[m]);
+        const size_t c1 = (size_t)nmod * (nk * (size_t)nit * ntile_n * I8_BK + (size_t)qc * nit * ntile_n);
+        const size_t c2 = (size_t)nmod * (nk * (size_t)nit_p * ntile_p * I8_BK + (size_t)qc * nit_p * ntile_p);
+        return std::max(c1, c2);
+    };
+    size_t planes_all = 0, cgws_all = 0, max_block = 0;
+    for (int m = 0; m < nbf; m++) {
+        planes_all += planes_of(m);
+        cgws_all += cgws_of(m);
+        max_block = std::max(max_block, planes_of(m) + cgws_of(m));
+    }
+    int m_r = 0;
+    size_t resident_bytes = 0;
+    if (planes_all + cgws_all + slack + align <= pl.arena_cap) {
+        m_r = nbf;
+        resident_bytes = planes_all;
+    } else if (resident_env) {
+        const size_t work = std::max(pl.arena_cap / 5, 2 * max_block + slack);
+        if (work + align < pl.arena_cap) {
+            const size_t room = pl.arena_cap - work - align;
+            while (m_r < nbf && resident_bytes + planes_of(m_r) <= room) resident_bytes += planes_of(m_r++);
+        }
+    }
+    const size_t work_off = (resident_bytes + align - 1) / align * align;
+    if (work_off + max_block + slack > pl.arena_cap) {
+        if (err) *err = "scratch arena too small for one row-block of residue planes";
         return 3;
     }
-    const bool cached = chunks.size() == 1 && i8h_cached(pl, which, qbeg, qc, nmod);
-    if (cached && fuse && !fuse_col) {
-        if (err) *err = "the first J sweep cannot ride on a conversion that is skipped (planes cached)";
+    const size_t work_cap = pl.arena_cap - work_off - slack;
+    struct Chunk {
+        int m0, m1;
+        bool resident;
+    };
+    std::vector<Chunk> chunks;
+    for (int part = 0; part < 2; part++) {
+        const int lo = part == 0 ? 0 : m_r, hi = part == 0 ? m_r : nbf;
+        int m0 = lo;
+        size_t cost = 0;
+        for (int m = lo; m < hi; m++) {
+            const size_t c = cgws_of(m) + (part == 0 ? 0 : planes_of(m));
+            if (m > m0 && cost + c > work_cap) {
+                chunks.push_back(Chunk{m0, m, part == 0});
+                m0 = m;
+                cost = 0;
+            }
+            cost += c;
+        }
+        if (hi > m0) chunks.push_back(Chunk{m0, hi, part == 0});
+    }
+    const size_t resident_stride = (size_t)pl.kboff[m_r] * (size_t)nqt * I8H_TILE;  // one resident plane
+    const bool cached = m_r > 0 && pl.arena && pl.cache_which == which && pl.cache_qbeg == qbeg && pl.cache_qc == qc &&
+                        pl.cache_nmod == nmod && pl.cache_mr == m_r && pl.expo_valid[which] && pl.expo_nmod[which] == nmod;
+    if (fuse && !fuse_col && m_r > 0) {
+        if (err) *err = "the first J sweep cannot ride on a conversion that is skipped (planes resident)";
         return 2;
     }
     if (!cached) pl.cache_which = -1;
     int nch = 0;
+    double converted_sp = 0, converted_planes = 0;
     for (auto& c : chunks) {
         const int nmc = c.m1 - c.m0;
+        const size_t nkb_c = (size_t)(pl.kboff[c.m1] - pl.kboff[c.m0]);
         const bool prof = pl.prof[0] && nch == 0;
+        const bool convert = !(c.resident && cached);
+        // carve: resident chunk = planes in the resident region, C^T | residues in the work region; otherwise all three there
+        int8_t* planes;
+        size_t plane_stride;
+        uint8_t* wbase = pl.arena + work_off;
+        if (c.resident) {
+            planes = reinterpret_cast<int8_t*>(pl.arena) + (size_t)pl.kboff[c.m0] * (size_t)nqt * I8H_TILE;
+            plane_stride = resident_stride;
+        } else {
+            planes = reinterpret_cast<int8_t*>(wbase);
+            plane_stride = nkb_c * (size_t)nqt * I8H_TILE;
+            wbase += plane_stride * nmod;
+        }
+        const size_t cg_plane = nkb_c * (size_t)nit * ntile_n * I8_BK;
+        int8_t* cg = reinterpret_cast<int8_t*>(wbase);
+        uint8_t* ws = wbase + cg_plane * nmod;
+        if ((size_t)(ws - pl.arena) + (size_t)nmod * nmc * qc * opw > pl.arena_cap) {
+            if (err) *err = "scratch arena accounting";
+            return 3;
+        }
         if (prof) cudaEventRecord(pl.prof[0], st);
         if (pl.mark) pl.mark(pl.mark_ctx, 10);
-        if (cached) pl.conversions_skipped++;
+        if (!convert) pl.conversions_skipped++;
         I8HalfFuseJ fjv = {nullptr, 0, nullptr, 0, nullptr, nullptr};
         if (fuse && !fuse_col) {
             fjv = *fuse;
             fjv.cols = d_cols;
             fjv.cols_off = d_cols_off;
         }
-        if (!cached)
+        if (convert) {
             I8H_DISPATCH(nmod, i8h_launch_convert, tensor, d_row_off, d_ldm, d_sp, pl.d_kboff, pl.expoB[which], nq, c.m0, nmc, qbeg, qc, nqt,
                          planes, plane_stride, fjv, pl.max_nkb_row, st);
+            converted_sp += pl.sp_prefix[c.m1] - pl.sp_prefix[c.m0];
+            converted_planes += (double)nmod * nqt * (double)nkb_c * I8H_TILE;
+        }
         if (prof) cudaEventRecord(pl.prof[1], st);
         if (pl.mark) pl.mark(pl.mark_ctx, 11);
         static int gather_word = -1;
@@ -919,14 +994,13 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
             const char* e = getenv("B200JK_I8_GATHER");
             gather_word = (e && !strcmp(e, "word")) ? 1 : 0;
         }
-        if (!fuse_col && (gather_word || (size_t)pl.max_nkb_row * I8_BK * sizeof(int) > 48 * 1024))
+        if (!fuse_col && (gather_word || i8g_smem_bytes(pl.max_nkb_row, rc_ld) > 48 * 1024))
             i8h_gather_kernel<<<dim3((unsigned)nmc, (unsigned)((opw + 3) / 4)), 128, 0, st>>>(pl.rc, rc_ld, rc_plane, o, nmod, d_sp, pl.d_kboff,
                                                                                             d_cols, d_cols_off, c.m0, nit, ntile_n, cg, cg_plane);
         else
-            i8h_gather16_kernel<<<dim3((unsigned)nmc, (unsigned)((opw + I8G_ROWS - 1) / I8G_ROWS)), 256,
-                                  (size_t)pl.max_nkb_row * I8_BK * sizeof(int), st>>>(pl.rc, rc_ld, rc_plane, o, nmod, d_sp, pl.d_kboff, d_cols,
-                                                                                      d_cols_off, c.m0, nit, ntile_n, cg, cg_plane,
-                                                                                      fuse_col ? pl.rD : nullptr, rd_plane, fuse_col ? o : -1);
+            i8h_gather16_kernel<<<dim3((unsigned)nmc, (unsigned)((opw + I8G_ROWS - 1) / I8G_ROWS)), 256, i8g_smem_bytes(pl.max_nkb_row, rc_ld),
+                                  st>>>(pl.rc, rc_ld, rc_plane, o, nmod, d_sp, pl.d_kboff, d_cols, d_cols_off, c.m0, nit, ntile_n, cg, cg_plane,
+                                        fuse_col ? pl.rD : nullptr, rd_plane, fuse_col ? o : -1, pl.max_nkb_row);
         if (prof) cudaEventRecord(pl.prof[2], st);
         if (pl.mark) pl.mark(pl.mark_ctx, 12);
         I8HalfParams gp;
@@ -992,14 +1066,17 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
         I8CK(cudaGetLastError());
         nch++;
     }
-    if (chunks.size() == 1) {
+    if (m_r > 0) {
         pl.cache_which = which;
         pl.cache_qbeg = qbeg;
         pl.cache_qc = qc;
         pl.cache_nmod = nmod;
+        pl.cache_mr = m_r;
     }
     if (info) {
-        info->cached = cached ? 1 : 0;
+        info->cached = (cached && m_r == nbf) ? 1 : 0;
+        info->resident_rows = m_r;
+        info->resident_hit = cached ? 1 : 0;
         info->nmod = nmod;
         info->nchunks = nch;
         info->ntile_n = ntile_n;
@@ -1010,7 +1087,7 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
         const double nkb_all = (double)pl.kboff[nbf];
         info->mma_ops = 2.0 * nmod * ((double)((nqt + cluster - 1) / cluster * cluster) * I8_TM) * (nkb_all * I8_BK) * ((double)nit * ntile_n);
         info->plane_bytes = (double)nmod * nqt * nkb_all * I8H_TILE;
-        info->convert_bytes = cached ? 0.0 : 8.0 * qc * pl.sum_sp + info->plane_bytes;
+        info->convert_bytes = 8.0 * qc * converted_sp + converted_planes;
     }
     return 0;
 }

@@ -30,7 +30,7 @@ class Stats(ct.Structure):
         ("reduce_kind", ct.c_int), ("kgemm_kind", ct.c_int), ("kgemm_moduli", ct.c_int), ("half_kind", ct.c_int),
         ("ms_half_i8", ct.c_double * 4), ("ms_kgemm_i8", ct.c_double * 3), ("half_i8_ops", ct.c_double),
         ("half_i8_plane_bytes", ct.c_double), ("half_i8_convert_bytes", ct.c_double), ("kgemm_i8_ops", ct.c_double),
-        ("half_moduli", ct.c_int), ("half_i8_chunks", ct.c_int), ("half_i8_cached", ct.c_int), ("reserved_", ct.c_int),
+        ("half_moduli", ct.c_int), ("half_i8_chunks", ct.c_int), ("half_i8_cached", ct.c_int), ("half_i8_resident_rows", ct.c_int),
     ]
 
     def as_dict(self):

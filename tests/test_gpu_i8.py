@@ -301,3 +301,76 @@ def test_i8_first_j_sweep_rides_on_the_gemm(oracle):
     check(J, Jo, what="J general")
     check(K, Ko, what="K general")
     e.close()
+
+
+RESIDENT_SCRIPT = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.environ["B2_ROOT"]); sys.path.insert(0, os.path.join(os.environ["B2_ROOT"], "oracle"))
+import dfjk_oracle as oracle
+from psi4_b200 import DFHelper, Engine
+rng = np.random.default_rng(31)
+n, a = 300, 200
+r = rng.random((n, n)); keep = (r + r.T) < 1.2; np.fill_diagonal(keep, True)
+d = DFHelper(n, a); d.prepare_sparsity(keep=keep)
+B = rng.standard_normal((a, n, n)) * 0.1; B = B + B.transpose(0, 2, 1)
+P = d.pack(B)
+Cl = [np.linalg.qr(rng.standard_normal((n, o)))[0] for o in (40, 33)]
+D = [2.0 * c @ c.T for c in Cl]
+Jo, Ko, _, _ = oracle.build_JK(oracle.Sparsity(keep, a), P, Cl, D=D)
+e = Engine(1); e.set_layout(n, a, d.small_skips_, d.big_skips_, d.schwarz_fun_index_); e.upload(0, P)
+e.set_half("i8"); e.set_kgemm("i8")
+res = []
+for it in range(3):
+    J, K, _ = e.compute(Cl, None, D)
+    st = e.stats()
+    res.append(([x.copy() for x in J], [x.copy() for x in K], st))
+    err = max(max(np.abs(x - y).max() for x, y in zip(J, Jo)), max(np.abs(x - y).max() for x, y in zip(K, Ko)))
+    print(f"build {it}: err {err:.3e} resident {st['half_i8_resident_rows']} chunks {st['half_i8_chunks']} "
+          f"convert_bytes {st['half_i8_convert_bytes']:.3e} cached {st['half_i8_cached']}")
+    assert err < 1e-10 and st["half_kind"] == 1
+want = os.environ["EXPECT"]
+rows = res[0][2]["half_i8_resident_rows"]
+if want == "partial":
+    assert 0 < rows < n, rows
+    assert res[0][2]["half_i8_chunks"] > 2 * 2          # several chunks per transform
+    # the second build converts only what is not resident; the first one converted everything (twice: the resident part is
+    # valid for the second density already)
+    assert 0 < res[1][2]["half_i8_convert_bytes"] < res[0][2]["half_i8_convert_bytes"]
+elif want == "none":
+    assert rows == 0 and res[1][2]["half_i8_convert_bytes"] == res[0][2]["half_i8_convert_bytes"] > 0
+else:
+    assert rows == n and res[1][2]["half_i8_convert_bytes"] == 0
+for it in (1, 2):  # resident or not, converted in this build or in an earlier one: the same bits
+    for x, y in zip(res[0][0] + res[0][1], res[it][0] + res[it][1]):
+        assert np.array_equal(x, y)
+# a new tensor invalidates the resident planes
+P2 = d.pack(B * 1.5)
+e.upload(0, P2)
+J, K, _ = e.compute(Cl, None, D)
+Jo2, Ko2, _, _ = oracle.build_JK(oracle.Sparsity(keep, a), P2, Cl, D=D)
+err = max(max(np.abs(x - y).max() for x, y in zip(J, Jo2)), max(np.abs(x - y).max() for x, y in zip(K, Ko2)))
+print(f"new tensor: err {err:.3e}")
+assert err < 1e-10
+e.close()
+"""
+
+
+@pytest.mark.parametrize("env,expect", [({"B200JK_I8_ARENA_MB": "150"}, "partial"),
+                                        ({"B200JK_I8_ARENA_MB": "150", "B200JK_I8_RESIDENT": "0"}, "none"),
+                                        ({"B200JK_I8_ARENA_MB": "60", "B200JK_I8_JCOL": "0"}, "partial"),
+                                        ({}, "all")])
+def test_i8_half_partly_resident_planes(tmp_path, env, expect):
+    """The scratch arena of the residue half transform holds the planes of the first row-blocks for good and converts the
+    rest in every build (i8_half_run: resident region + work region).  Forced here by a small arena on a small system:
+    J / K against the oracle over three builds and two densities, bit-identical across builds whatever was resident,
+    with the A/B switches (nothing resident; the first J sweep as its own kernel), and after the tensor is replaced."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "resident.py"
+    script.write_text(RESIDENT_SCRIPT)
+    r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, B2_ROOT=root, EXPECT=expect, **env), capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2500:] + r.stderr[-2500:]
