@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) i8h_rowscale_kernel(const double* __restr
 // makes it), lane partials in k order, xor-shuffle tree: a fixed order.  Dm == nullptr: plain conversion.
 //
 // gemm_col = 1: the sweep rides on the GEMM instead -- the density row of row-block m, as residues, is gathered into the first
-// free column (index nocc) of the row-block's C^T tile, the GEMM computes it like any orbital, and i8h_dq_kernel rebuilds
+// free column (index nocc) of the row-block's C^T tile, the GEMM computes it like any orbital, and the CRT kernel rebuilds
 //   dpart[m][q] = sum_k B'_m[q,k] D'[m,n_k] * 2^-(eB(m,q) + eD(m))
 // from the residues: exact in the integers, so the same bits whether the planes were converted in this build or cached from
 // an earlier one (a sweep riding on the conversion cannot be used when the conversion is skipped).
@@ -211,22 +211,22 @@ __global__ void __launch_bounds__(128) i8h_gather_kernel(const int8_t* __restric
     }
 }
 
-// The same gather in 16-byte units through shared memory (the default; B200JK_I8_GATHER=word keeps the word-wise kernel
-// above for A/B).  The word-wise kernel took 3.0 ms per build whatever the shard size (1.9 TB/s of stores): a fifth of the
-// whole build on the 592-row shard of the 8-GPU run, and ncu shows it waiting on its own loads (long-scoreboard stalls,
-// 26 % issue-active): every 4 output bytes cost two dependent L2 accesses.  Here a CTA takes 16 orbital rows of one
-// row-block; per modulus it stages those 16 rows of the residue plane (16 x nbf bytes, L2-resident source) in shared
-// memory with coalesced 16-byte loads, and one thread then owns one 16-byte chunk (16 consecutive k) of one orbital row:
-// a chunk whose partners are consecutive columns (first and last differ by 15: the list is sorted) is one unaligned
-// 16-byte window of the staged row -- five shared-memory words and four funnel shifts -- and a warp stores four whole
-// 128-byte tile rows (512 contiguous bytes).  The row pitch is 9 words modulo 32, which spreads the 4 rows x 8 chunks a
-// warp reads at a time over all 32 banks.
+// The same gather through shared memory (the default; B200JK_I8_GATHER=word keeps the kernel above for A/B).  The kernel
+// above took 3.0 ms per build whatever the shard size (1.9 TB/s of stores): a fifth of the whole build on the 592-row
+// shard of the 8-GPU run, and ncu shows it waiting on its own loads (long-scoreboard stalls, 26 % issue-active): every 4
+// output bytes cost two dependent L2 accesses.  Here a CTA takes 16 orbital rows of one row-block; per modulus it stages
+// those 16 rows of the residue plane (16 x nbf bytes, L2-resident source) in shared memory with coalesced 16-byte loads,
+// and one thread then owns one 4-byte word (4 consecutive k) of one orbital row -- a warp one whole 128-byte tile row:
+// its four partners come as one 16-byte read of the list; when they are consecutive columns (kept partners come in runs,
+// but at C60 mostly shorter than 16: a 16-byte unit was tried and ran mostly on its slow path) the word is one unaligned
+// window of the staged row (two words and a funnel shift), four byte reads otherwise.
 // grid (nmc, ceil(opw / I8G_ROWS)), 256 threads, dynamic shared memory i8g_smem_bytes().
 constexpr int I8G_ROWS = 16;
-__host__ __device__ inline size_t i8g_pitch_words(size_t rc_ld) { return rc_ld / 4 + 8 + 1; }  // >= 16 bytes of over-read room; = 9 (mod 32) as rc_ld % 128 == 0
+__host__ __device__ inline size_t i8g_pitch_words(size_t rc_ld) { return rc_ld / 4 + 1; }  // one word of over-read room; odd: rows spread over the banks
 inline size_t i8g_smem_bytes(int max_nkb, size_t rc_ld) {
     return (size_t)max_nkb * I8_BK * sizeof(int) + (size_t)I8G_ROWS * i8g_pitch_words(rc_ld) * 4;
 }
+constexpr size_t I8G_SMEM_MAX = 96 * 1024;  // opt-in dynamic shared memory of the gather: nbf up to ~4700
 __global__ void __launch_bounds__(256) i8h_gather16_kernel(const int8_t* __restrict__ rc, size_t rc_ld, size_t rc_plane, int o, int nmod,
                                                            const int* __restrict__ sp, const int* __restrict__ kboff,
                                                            const int* __restrict__ cols, const size_t* __restrict__ cols_off, int m0,
@@ -244,23 +244,26 @@ __global__ void __launch_bounds__(256) i8h_gather16_kernel(const int8_t* __restr
     const size_t blk = (size_t)ntile_n * I8_BK;
     int8_t* base = cg + (size_t)(kboff[m] - kboff[m0]) * nit * blk;
     const int i0 = blockIdx.y * I8G_ROWS, opw = nit * ntile_n;
-    const int nunit = nk * I8G_ROWS * 8;
+    const int nunit = nk * I8G_ROWS * 32;  // (k-block, row, word)
     const int vec_per_row = (int)(rc_ld / 16);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int j = 0; j < nmod; j++) {
         __syncthreads();  // the list is written (j = 0) / the rows of the previous modulus have been read
-        for (int v = threadIdx.x; v < I8G_ROWS * vec_per_row; v += 256) {
-            const int rr = v / vec_per_row, x = v - rr * vec_per_row;
+        // stage: a warp takes two rows, 16 bytes per lane and step (coalesced), stored as four words rotated by the lane's
+        // octet so that lanes l, l+8, l+16, l+24 (the same bank otherwise) hit four banks
+        for (int rr = warp; rr < I8G_ROWS; rr += 8) {
             const int i = i0 + rr;
             const int8_t* src = nullptr;
             if (i < o)
                 src = rc + (size_t)j * rc_plane + (size_t)i * rc_ld;
             else if (i == dcol)
                 src = rD + (size_t)j * rd_plane + (size_t)m * rc_ld;
-            if (src) {
+            if (!src) continue;
+            uint32_t* drow = rows + rr * pitchw;
+            const int rot = (lane >> 3) & 3;
+            for (int x = lane; x < vec_per_row; x += 32) {
                 const uint4 q = *reinterpret_cast<const uint4*>(src + (size_t)x * 16);
-                uint32_t* dst = rows + rr * pitchw + x * 4;
-                // the four words go out rotated by the lane's octet: lanes l, l+8, l+16, l+24 (same bank otherwise) hit four banks
-                const int rot = (threadIdx.x >> 3) & 3;
+                uint32_t* dst = drow + x * 4;
 #pragma unroll
                 for (int t = 0; t < 4; t++) {
                     const int w = (rot + t) & 3;
@@ -269,39 +272,28 @@ __global__ void __launch_bounds__(256) i8h_gather16_kernel(const int8_t* __restr
             }
         }
         __syncthreads();
+        int8_t* basej = base + (size_t)j * cg_plane;
         for (int u = threadIdx.x; u < nunit; u += 256) {
-            const int ch = u & 7, rowi = (u >> 3) & (I8G_ROWS - 1), kb = u >> 7;  // I8G_ROWS * 8 = 128 units per k-block
+            const int w = u & 31, rowi = (u >> 5) & (I8G_ROWS - 1), kb = u >> 9;  // I8G_ROWS * 32 = 512 units per k-block
             const int i = i0 + rowi;
             if (i >= opw) continue;
             const int il = i / ntile_n, row = i - il * ntile_n;
-            const int* id = i8g_idx + kb * I8_BK + ch * 16;
-            const int n0 = id[0];
-            uint4* d = reinterpret_cast<uint4*>(base + ((size_t)kb * nit + il) * blk + row * I8_BK + ((ch ^ (row & 7)) << 4) + (size_t)j * cg_plane);
-            if ((i >= o && i != dcol) || n0 < 0) {  // a column beyond nocc, or a chunk wholly beyond sp(m) (the list ends in -1 padding)
-                *d = make_uint4(0u, 0u, 0u, 0u);
-                continue;
-            }
-            const uint32_t* srow = rows + rowi * pitchw;
-            if (id[15] == n0 + 15) {
-                const int sh = (n0 & 3) * 8;
-                const uint32_t* w = srow + (n0 >> 2);
-                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];  // w[4]: inside the padded row
-                uint4 v;
-                v.x = __funnelshift_r(w0, w1, sh);
-                v.y = __funnelshift_r(w1, w2, sh);
-                v.z = __funnelshift_r(w2, w3, sh);
-                v.w = __funnelshift_r(w3, w4, sh);
-                *d = v;
-            } else {
-                const uint8_t* sb = reinterpret_cast<const uint8_t*>(srow);
-                uint32_t v[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-                for (int e = 0; e < 16; e++) {
-                    const int n = id[e];
-                    if (n >= 0) v[e >> 2] |= ((uint32_t)sb[n]) << (8 * (e & 3));
+            const int4 n = *reinterpret_cast<const int4*>(i8g_idx + kb * I8_BK + w * 4);
+            uint32_t v = 0u;
+            if ((i < o || i == dcol) && n.x >= 0) {  // else: a column beyond nocc / a word wholly beyond sp(m) (the list ends in -1 padding)
+                const uint32_t* srow = rows + rowi * pitchw;
+                if (n.w == n.x + 3) {
+                    const uint32_t* p = srow + (n.x >> 2);
+                    v = __funnelshift_r(p[0], p[1], (n.x & 3) * 8);  // p[1]: at worst the pad word of the row
+                } else {
+                    const uint8_t* sb = reinterpret_cast<const uint8_t*>(srow);
+                    v = (uint32_t)sb[n.x];
+                    if (n.y >= 0) v |= (uint32_t)sb[n.y] << 8;
+                    if (n.z >= 0) v |= (uint32_t)sb[n.z] << 16;
+                    if (n.w >= 0) v |= (uint32_t)sb[n.w] << 24;
                 }
-                *d = make_uint4(v[0], v[1], v[2], v[3]);
             }
+            *reinterpret_cast<uint32_t*>(basej + ((size_t)kb * nit + il) * blk + row * I8_BK + (((w >> 2) ^ (row & 7)) << 4) + ((w & 3) << 2)) = v;
         }
     }
 }
@@ -534,6 +526,11 @@ struct I8HalfCrtParams {
     const int *eB, *eC;
     double* T;
     unsigned long long M_lo, M_hi, H_lo, H_hi;
+    // first J sweep riding on the GEMM (I8HalfFuseJ::gemm_col): column dcol (>= o; -1: none) holds the residues of
+    // sum_k B'_m[q,k] D'[m,n_k]; the value, * 2^-(eB(m,q) + eD(m)), goes to dpart[m * dstride + qbeg + q]
+    int dcol, dstride;
+    const int* eD;
+    double* dpart;
 };
 // grid (ceil(qc * opw / 4 / 256), nmc): one thread = four consecutive orbitals of one (m, q)
 template <int NMOD>
@@ -541,7 +538,7 @@ __global__ void __launch_bounds__(256) i8h_crt_kernel(const I8HalfCrtParams p) {
     const int per_q = p.opw >> 2;
     const long idx = (long)blockIdx.x * 256 + threadIdx.x;
     const int q = (int)(idx / per_q), i4 = (int)(idx - (long)q * per_q) * 4;
-    if (q >= p.qc || i4 >= p.op) return;
+    if (q >= p.qc || (i4 >= p.op && !(p.dcol >= i4 && p.dcol < i4 + 4))) return;
     const int mloc = blockIdx.y, m = p.m0 + mloc;
     const uint8_t* src = p.ws + ((size_t)mloc * p.qc + q) * p.opw + i4;
     uint32_t w[NMOD];
@@ -552,7 +549,15 @@ __global__ void __launch_bounds__(256) i8h_crt_kernel(const I8HalfCrtParams p) {
 #pragma unroll
     for (int c = 0; c < 4; c++) {
         const int i = i4 + c;
-        if (i >= p.op) break;
+        if (i == p.dcol) {
+            int rr[NMOD];
+#pragma unroll
+            for (int j = 0; j < NMOD; j++) rr[j] = (int)((w[j] >> (8 * c)) & 255u);
+            const int e2 = -(eb + p.eD[m]);
+            const double f = i8_crt_value_fast<NMOD>(rr);
+            p.dpart[(size_t)m * p.dstride + p.qbeg + q] = (e2 > -1000 && e2 < 1000) ? f * __hiloint2double((1023 + e2) << 20, 0) : ldexp(f, e2);
+        }
+        if (i >= p.op) continue;
         double val = 0.0;
         if (i < p.o) {
             int rr[NMOD];
@@ -566,30 +571,6 @@ __global__ void __launch_bounds__(256) i8h_crt_kernel(const I8HalfCrtParams p) {
         }
         dst[c] = val;
     }
-}
-
-// First J sweep from the GEMM's extra column (I8HalfFuseJ::gemm_col): one thread per (row-block, q).
-struct I8HalfDqParams {
-    const uint8_t* ws;
-    size_t ws_mod_stride;
-    int opw, col, qc, qbeg, nq, m0, dstride;
-    const int *eB, *eD;
-    double* dpart;
-};
-template <int NMOD>
-__global__ void __launch_bounds__(256) i8h_dq_kernel(const I8HalfDqParams p) {
-    const int q = blockIdx.x * 256 + threadIdx.x;
-    if (q >= p.qc) return;
-    const int mloc = blockIdx.y, m = p.m0 + mloc;
-    const uint8_t* src = p.ws + ((size_t)mloc * p.qc + q) * p.opw + p.col;
-    int rr[NMOD];
-#pragma unroll
-    for (int j = 0; j < NMOD; j++) rr[j] = (int)src[(size_t)j * p.ws_mod_stride];
-    p.dpart[(size_t)m * p.dstride + p.qbeg + q] = ldexp(i8_crt_value_fast<NMOD>(rr), -(p.eB[(size_t)m * p.nq + p.qbeg + q] + p.eD[m]));
-}
-template <int NMOD>
-inline void i8h_launch_dq(const I8HalfDqParams& p, int nmc, cudaStream_t st) {
-    i8h_dq_kernel<NMOD><<<dim3((unsigned)((p.qc + 255) / 256), (unsigned)nmc), 256, 0, st>>>(p);
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------------------
@@ -720,10 +701,12 @@ inline void i8h_launch_crt(const I8HalfCrtParams& p, int nmc, cudaStream_t st) {
 
 template <int CL>
 inline int i8h_launch_gemm(const I8HalfParams& gp, int nsm, cudaStream_t st, std::string* err) {
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {false};  // function attributes are per device: one process may drive all eight
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr[dev & 63]) {
         I8CK(cudaFuncSetAttribute(i8h_gemm_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)i8_smem_bytes()));
-        attr = true;
+        attr[dev & 63] = true;
     }
     if (CL == 1) {
         i8h_gemm_kernel<CL><<<(unsigned)std::min(gp.nitems, nsm), I8_THREADS, i8_smem_bytes(), st>>>(gp);
@@ -783,7 +766,7 @@ inline bool i8h_can_fuse_col(const I8HalfPlan& pl, int o, int cluster) {
     i8h_tiling(o, cluster, &nit, &ntile_n);
     const char* e = getenv("B200JK_I8_GATHER");
     const size_t rc_ld = (pl.kboff.size() - 1 + 127) / 128 * 128;
-    return o > 0 && o < nit * ntile_n && !(e && !strcmp(e, "word")) && i8g_smem_bytes(pl.max_nkb_row, rc_ld) <= 48 * 1024;
+    return o > 0 && o < nit * ntile_n && !(e && !strcmp(e, "word")) && i8g_smem_bytes(pl.max_nkb_row, rc_ld) <= I8G_SMEM_MAX;
 }
 
 // bytes of arena one row-block with nkb k-blocks needs
@@ -841,6 +824,7 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
         pl.launches++;
         pl.expo_valid[which] = true;
         pl.expo_nmod[which] = nmod;
+        if (pl.cache_which == which) pl.cache_which = -1;  // the tensor changed: its resident planes are stale too
     }
     // C operand: column scales and residue planes rc[j][i][n] (the row kernels of i8_kgemm.cuh on the rows of C^T)
     const size_t rc_ld = ((size_t)nbf + 127) / 128 * 128, rc_plane = rc_ld * (size_t)o;
@@ -994,13 +978,21 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
             const char* e = getenv("B200JK_I8_GATHER");
             gather_word = (e && !strcmp(e, "word")) ? 1 : 0;
         }
-        if (!fuse_col && (gather_word || i8g_smem_bytes(pl.max_nkb_row, rc_ld) > 48 * 1024))
+        if (!fuse_col && (gather_word || i8g_smem_bytes(pl.max_nkb_row, rc_ld) > I8G_SMEM_MAX))
             i8h_gather_kernel<<<dim3((unsigned)nmc, (unsigned)((opw + 3) / 4)), 128, 0, st>>>(pl.rc, rc_ld, rc_plane, o, nmod, d_sp, pl.d_kboff,
                                                                                             d_cols, d_cols_off, c.m0, nit, ntile_n, cg, cg_plane);
-        else
+        else {
+            static bool gattr[64] = {false};  // per device
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (!gattr[dev & 63]) {
+                I8CK(cudaFuncSetAttribute(i8h_gather16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8G_SMEM_MAX));
+                gattr[dev & 63] = true;
+            }
             i8h_gather16_kernel<<<dim3((unsigned)nmc, (unsigned)((opw + I8G_ROWS - 1) / I8G_ROWS)), 256, i8g_smem_bytes(pl.max_nkb_row, rc_ld),
                                   st>>>(pl.rc, rc_ld, rc_plane, o, nmod, d_sp, pl.d_kboff, d_cols, d_cols_off, c.m0, nit, ntile_n, cg, cg_plane,
                                         fuse_col ? pl.rD : nullptr, rd_plane, fuse_col ? o : -1, pl.max_nkb_row);
+        }
         if (prof) cudaEventRecord(pl.prof[2], st);
         if (pl.mark) pl.mark(pl.mark_ctx, 12);
         I8HalfParams gp;
@@ -1042,27 +1034,14 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
         cp.M_hi = (unsigned long long)(M >> 64);
         cp.H_lo = (unsigned long long)(M / 2);
         cp.H_hi = (unsigned long long)((M / 2) >> 64);
+        cp.dcol = fuse_col ? o : -1;
+        cp.dstride = fuse_col ? fuse->dstride : 0;
+        cp.eD = pl.expoD;
+        cp.dpart = fuse_col ? fuse->dpart : nullptr;
         I8H_DISPATCH(nmod, i8h_launch_crt, cp, nmc, st);
-        if (fuse_col) {
-            I8HalfDqParams dp;
-            dp.ws = ws;
-            dp.ws_mod_stride = gp.ws_mod_stride;
-            dp.opw = opw;
-            dp.col = o;
-            dp.qc = qc;
-            dp.qbeg = qbeg;
-            dp.nq = nq;
-            dp.m0 = c.m0;
-            dp.dstride = fuse->dstride;
-            dp.eB = pl.expoB[which];
-            dp.eD = pl.expoD;
-            dp.dpart = fuse->dpart;
-            I8H_DISPATCH(nmod, i8h_launch_dq, dp, nmc, st);
-            pl.launches++;
-        }
         if (prof) cudaEventRecord(pl.prof[4], st);
         if (pl.mark) pl.mark(pl.mark_ctx, 14);
-        pl.launches += 4;
+        pl.launches += convert ? 4 : 3;
         I8CK(cudaGetLastError());
         nch++;
     }
