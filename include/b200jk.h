@@ -248,8 +248,14 @@ int b200jk_set_kgemm(b200jk_t* h, int arm, int moduli);
  * lib3index/dfhelper.cc:2162-2186): arm 0 automatic, 1 FP64 tensor pipe (half_ws_kernel), 2 INT8 tensor cores.  The
  * residue arm scales every row (m,Q) of the resident tensor (once per tensor) and every column of C (once per build) to
  * integers, multiplies modulo `moduli` coprime numbers (default 12: 46.9 bits below |B[Q,m,:]| |C[:,i]|) and rebuilds T
- * by the Chinese remainder theorem.  The first J sweep rides on the conversion of the tensor rows instead of on the GEMM.
- * Environment: B200JK_HALF=dmma|i8, B200JK_I8_HALF_MODULI=n, B200JK_I8_CLUSTER=1|2|4. */
+ * by the Chinese remainder theorem.  automatic = from 256 basis functions, 16 occupied orbitals and 2^27 tensor elements per
+ * shard on.  The residue planes of as many row-blocks as the scratch arena holds stay in HBM until the tensor changes (all of
+ * them from two GPUs on at C60; stats.half_i8_resident_rows), the rest is converted in every build.  The first J sweep is one
+ * more column of the residue GEMM (the density row of each row-block; needs nocc not a multiple of 16), with the arm's
+ * norm-wise error 2^-46.9 |B[Q,m,:]| |D'[m,:]|.
+ * Environment: B200JK_HALF=dmma|i8, B200JK_I8_HALF_MODULI=n, B200JK_I8_CLUSTER=1|2|4, B200JK_I8_RESIDENT=0 (planes resident only
+ * when all of them fit), B200JK_I8_JCOL=0 (first J sweep as its own FP64 kernel), B200JK_I8_ARENA_MB=n (upper bound of the
+ * scratch arena; tests). */
 int b200jk_set_half(b200jk_t* h, int arm, int moduli);
 
 /* ---- synthetic workload support (bench.py / large-size tests only; not in the reference) ------ */

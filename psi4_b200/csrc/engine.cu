@@ -169,6 +169,7 @@ struct Shard {
     std::vector<std::pair<int, cudaEvent_t>> marks;
     double i8h_ops = 0, i8h_plane_bytes = 0, i8h_convert_bytes = 0, i8k_ops = 0;
     int i8h_nmod = 0, i8h_chunks = 0, i8h_cached = 0, i8h_resident_rows = 0;
+    int i8k_ok_kdim = -1, i8k_ok_nop = 0, i8k_ok_nmod = 0;  // shape of the last K GEMM the residue arm completed (its buffers suffice)
 };
 }  // namespace
 
@@ -825,7 +826,11 @@ int run_kgemm_i8(b200jk* h, Shard& s, const double* T1, const double* T2, int kd
     const size_t ws_est = ((size_t)(kdim + klen - 1) / klen) * nmod * ntile_est * I8_TILE_BYTES;
     const size_t plane_need = (size_t)nmod * nbf * (((size_t)kdim + 127) / 128 * 128);  // per operand, one pass over k
     size_t budget = plane_need * nop;
-    const bool have = s.i8.planes_cap[0] >= plane_need && (nop == 1 || s.i8.planes_cap[1] >= plane_need) && s.i8.ws_cap >= ws_est;
+    // (ws_est is an upper estimate -- the symmetric tile list is about half of it -- so a workspace grown to what a build of
+    // this very shape needed counts as sufficient: otherwise every build would ask the driver for the free memory)
+    const bool same_shape = s.i8k_ok_kdim == kdim && s.i8k_ok_nop == nop && s.i8k_ok_nmod == nmod && s.i8.ws_cap > 0;
+    const bool have = s.i8.planes_cap[0] >= plane_need && (nop == 1 || s.i8.planes_cap[1] >= plane_need) &&
+                      (s.i8.ws_cap >= ws_est || same_shape);
     if (!have) {
         // (cudaMemGetInfo only when something must grow: in the steady state of an SCF it would be a driver call per build
         // that now and then waits tens of milliseconds behind the copies of the other stream)
@@ -854,6 +859,9 @@ int run_kgemm_i8(b200jk* h, Shard& s, const double* T1, const double* T2, int kd
     if (rc) return fail(h, B200JK_ERR_CUDA, "INT8 K GEMM: %s", err.c_str());
     s.kgemm_kind = 1;
     s.kgemm_moduli = info.nmod;
+    s.i8k_ok_kdim = kdim;
+    s.i8k_ok_nop = nop;
+    s.i8k_ok_nmod = nmod;
     s.i8k_ops += info.mma_ops;
     return 0;
 }

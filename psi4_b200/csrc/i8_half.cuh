@@ -166,10 +166,20 @@ __global__ void __launch_bounds__(256) i8h_convert_kernel(const double* __restri
 // block (m, kb, il) of plane j: cg + j * cg_plane + ((kboff[m] - kboff[m0] + kb) * nit + il) * ntile_n * 128, row = orbital
 // within the tile, byte kk = k % 128 at chunk (kk / 16) ^ (row & 7).  grid (nmc, ceil(opw / 4)); one thread = four
 // consecutive k of four orbitals, all moduli; k beyond sp(m) and orbitals beyond nocc are written as zeros.
-__global__ void __launch_bounds__(128) i8h_gather_kernel(const int8_t* __restrict__ rc, size_t rc_ld, size_t rc_plane, int o, int nmod,
+// rD / dcol: residue planes rD[j][m][n] of the density rows and the column (>= nocc) that carries row m of them in
+// row-block m's tile (first J sweep as a column of the GEMM, I8HalfFuseJ::gemm_col); dcol < 0: none.
+// The source planes (a few MB) live in L2 and every word costs two dependent accesses to it, so the loop over the moduli
+// is unrolled at compile time: all 2 * NMOD loads of an orbital are in flight before the first store (with a run-time
+// trip count ncu showed 26 % issue-active and 35 long-scoreboard stall cycles per instruction: 3.0 ms per build whatever
+// the shard size, a fifth of the build on the 592-row shard of the 8-GPU run).  Two variants through shared memory were
+// measured and dropped: a 16-byte unit (kept-partner runs at C60 are mostly shorter than 16: 4.2 ms on its byte path) and
+// a word unit with one staged modulus at a time (issue-bound on re-computed addresses: 5.9 ms).
+template <int NMOD>
+__global__ void __launch_bounds__(128) i8h_gather_kernel(const int8_t* __restrict__ rc, size_t rc_ld, size_t rc_plane, int o,
                                                          const int* __restrict__ sp, const int* __restrict__ kboff,
                                                          const int* __restrict__ cols, const size_t* __restrict__ cols_off, int m0,
-                                                         int nit, int ntile_n, int8_t* __restrict__ cg, size_t cg_plane) {
+                                                         int nit, int ntile_n, int8_t* __restrict__ cg, size_t cg_plane,
+                                                         const int8_t* __restrict__ rD, size_t rd_plane, int dcol) {
     const int m = m0 + blockIdx.x;
     const int K = sp[m], nk = kboff[m + 1] - kboff[m];
     const int* c = cols + cols_off[m];
@@ -191,111 +201,45 @@ __global__ void __launch_bounds__(128) i8h_gather_kernel(const int8_t* __restric
             if (i >= opw) break;
             const int il = i / ntile_n, row = i - il * ntile_n;
             int8_t* d = base + ((size_t)kb * nit + il) * blk + row * I8_BK + (((kk >> 4) ^ (row & 7)) << 4) + (kk & 15);
-            for (int j = 0; j < nmod; j++) {
-                uint32_t w = 0;
-                if (i < o) {
-                    const int8_t* src = rc + (size_t)j * rc_plane + (size_t)i * rc_ld;
-                    if (run) {
-                        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(src + nw);
-                        const uint32_t w1 = sh ? *reinterpret_cast<const uint32_t*>(src + nw + 4) : 0u;
-                        w = __funnelshift_r(w0, w1, sh);
-                    } else {
+            const bool isd = i == dcol;
+            const int8_t* src = isd ? rD + (size_t)m * rc_ld : rc + (size_t)i * rc_ld;
+            const size_t pstride = isd ? rd_plane : rc_plane;
+            uint32_t w[NMOD];
+            if ((i < o || isd) && n[0] >= 0) {
+                if (run) {
+                    uint32_t w0[NMOD], w1[NMOD];
+#pragma unroll
+                    for (int j = 0; j < NMOD; j++) {
+                        w0[j] = *reinterpret_cast<const uint32_t*>(src + (size_t)j * pstride + nw);
+                        w1[j] = sh ? *reinterpret_cast<const uint32_t*>(src + (size_t)j * pstride + nw + 4) : 0u;
+                    }
+#pragma unroll
+                    for (int j = 0; j < NMOD; j++) w[j] = __funnelshift_r(w0[j], w1[j], sh);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NMOD; j++) {
+                        uint32_t v = 0;
 #pragma unroll
                         for (int e = 0; e < 4; e++)
-                            if (n[e] >= 0) w |= ((uint32_t)(uint8_t)src[n[e]]) << (8 * e);
+                            if (n[e] >= 0) v |= ((uint32_t)(uint8_t)src[(size_t)j * pstride + n[e]]) << (8 * e);
+                        w[j] = v;
                     }
                 }
-                *reinterpret_cast<uint32_t*>(d + (size_t)j * cg_plane) = w;
-            }
-        }
-    }
-}
-
-// The same gather through shared memory (the default; B200JK_I8_GATHER=word keeps the kernel above for A/B).  The kernel
-// above took 3.0 ms per build whatever the shard size (1.9 TB/s of stores): a fifth of the whole build on the 592-row
-// shard of the 8-GPU run, and ncu shows it waiting on its own loads (long-scoreboard stalls, 26 % issue-active): every 4
-// output bytes cost two dependent L2 accesses.  Here a CTA takes 16 orbital rows of one row-block; per modulus it stages
-// those 16 rows of the residue plane (16 x nbf bytes, L2-resident source) in shared memory with coalesced 16-byte loads,
-// and one thread then owns one 4-byte word (4 consecutive k) of one orbital row -- a warp one whole 128-byte tile row:
-// its four partners come as one 16-byte read of the list; when they are consecutive columns (kept partners come in runs,
-// but at C60 mostly shorter than 16: a 16-byte unit was tried and ran mostly on its slow path) the word is one unaligned
-// window of the staged row (two words and a funnel shift), four byte reads otherwise.
-// grid (nmc, ceil(opw / I8G_ROWS)), 256 threads, dynamic shared memory i8g_smem_bytes().
-constexpr int I8G_ROWS = 16;
-__host__ __device__ inline size_t i8g_pitch_words(size_t rc_ld) { return rc_ld / 4 + 1; }  // one word of over-read room; odd: rows spread over the banks
-inline size_t i8g_smem_bytes(int max_nkb, size_t rc_ld) {
-    return (size_t)max_nkb * I8_BK * sizeof(int) + (size_t)I8G_ROWS * i8g_pitch_words(rc_ld) * 4;
-}
-constexpr size_t I8G_SMEM_MAX = 96 * 1024;  // opt-in dynamic shared memory of the gather: nbf up to ~4700
-__global__ void __launch_bounds__(256) i8h_gather16_kernel(const int8_t* __restrict__ rc, size_t rc_ld, size_t rc_plane, int o, int nmod,
-                                                           const int* __restrict__ sp, const int* __restrict__ kboff,
-                                                           const int* __restrict__ cols, const size_t* __restrict__ cols_off, int m0,
-                                                           int nit, int ntile_n, int8_t* __restrict__ cg, size_t cg_plane,
-                                                           const int8_t* __restrict__ rD, size_t rd_plane, int dcol, int max_nkb) {
-    // rD / dcol: residue planes rD[j][m][n] of the density rows and the column (>= nocc) that carries row m of them in
-    // row-block m's tile (first J sweep as a column of the GEMM); dcol < 0: none
-    extern __shared__ int i8g_idx[];  // [max_nkb * 128] kept partners of the row-block, -1 beyond sp(m); then the staged rows
-    const int pitchw = (int)i8g_pitch_words(rc_ld);
-    uint32_t* rows = reinterpret_cast<uint32_t*>(i8g_idx + (size_t)max_nkb * I8_BK);  // [I8G_ROWS][pitchw]
-    const int m = m0 + blockIdx.x;
-    const int K = sp[m], nk = kboff[m + 1] - kboff[m];
-    const int* c = cols + cols_off[m];
-    for (int k = threadIdx.x; k < nk * I8_BK; k += 256) i8g_idx[k] = k < K ? __ldg(c + k) : -1;
-    const size_t blk = (size_t)ntile_n * I8_BK;
-    int8_t* base = cg + (size_t)(kboff[m] - kboff[m0]) * nit * blk;
-    const int i0 = blockIdx.y * I8G_ROWS, opw = nit * ntile_n;
-    const int nunit = nk * I8G_ROWS * 32;  // (k-block, row, word)
-    const int vec_per_row = (int)(rc_ld / 16);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int j = 0; j < nmod; j++) {
-        __syncthreads();  // the list is written (j = 0) / the rows of the previous modulus have been read
-        // stage: a warp takes two rows, 16 bytes per lane and step (coalesced), stored as four words rotated by the lane's
-        // octet so that lanes l, l+8, l+16, l+24 (the same bank otherwise) hit four banks
-        for (int rr = warp; rr < I8G_ROWS; rr += 8) {
-            const int i = i0 + rr;
-            const int8_t* src = nullptr;
-            if (i < o)
-                src = rc + (size_t)j * rc_plane + (size_t)i * rc_ld;
-            else if (i == dcol)
-                src = rD + (size_t)j * rd_plane + (size_t)m * rc_ld;
-            if (!src) continue;
-            uint32_t* drow = rows + rr * pitchw;
-            const int rot = (lane >> 3) & 3;
-            for (int x = lane; x < vec_per_row; x += 32) {
-                const uint4 q = *reinterpret_cast<const uint4*>(src + (size_t)x * 16);
-                uint32_t* dst = drow + x * 4;
+            } else {
 #pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    const int w = (rot + t) & 3;
-                    dst[w] = w == 0 ? q.x : (w == 1 ? q.y : (w == 2 ? q.z : q.w));
-                }
+                for (int j = 0; j < NMOD; j++) w[j] = 0u;
             }
-        }
-        __syncthreads();
-        int8_t* basej = base + (size_t)j * cg_plane;
-        for (int u = threadIdx.x; u < nunit; u += 256) {
-            const int w = u & 31, rowi = (u >> 5) & (I8G_ROWS - 1), kb = u >> 9;  // I8G_ROWS * 32 = 512 units per k-block
-            const int i = i0 + rowi;
-            if (i >= opw) continue;
-            const int il = i / ntile_n, row = i - il * ntile_n;
-            const int4 n = *reinterpret_cast<const int4*>(i8g_idx + kb * I8_BK + w * 4);
-            uint32_t v = 0u;
-            if ((i < o || i == dcol) && n.x >= 0) {  // else: a column beyond nocc / a word wholly beyond sp(m) (the list ends in -1 padding)
-                const uint32_t* srow = rows + rowi * pitchw;
-                if (n.w == n.x + 3) {
-                    const uint32_t* p = srow + (n.x >> 2);
-                    v = __funnelshift_r(p[0], p[1], (n.x & 3) * 8);  // p[1]: at worst the pad word of the row
-                } else {
-                    const uint8_t* sb = reinterpret_cast<const uint8_t*>(srow);
-                    v = (uint32_t)sb[n.x];
-                    if (n.y >= 0) v |= (uint32_t)sb[n.y] << 8;
-                    if (n.z >= 0) v |= (uint32_t)sb[n.z] << 16;
-                    if (n.w >= 0) v |= (uint32_t)sb[n.w] << 24;
-                }
-            }
-            *reinterpret_cast<uint32_t*>(basej + ((size_t)kb * nit + il) * blk + row * I8_BK + (((w >> 2) ^ (row & 7)) << 4) + ((w & 3) << 2)) = v;
+#pragma unroll
+            for (int j = 0; j < NMOD; j++) *reinterpret_cast<uint32_t*>(d + (size_t)j * cg_plane) = w[j];
         }
     }
+}
+template <int NMOD>
+inline void i8h_launch_gather(const int8_t* rc, size_t rc_ld, size_t rc_plane, int o, const int* sp, const int* kboff, const int* cols,
+                              const size_t* cols_off, int m0, int nmc, int nit, int ntile_n, int8_t* cg, size_t cg_plane, const int8_t* rD,
+                              size_t rd_plane, int dcol, cudaStream_t st) {
+    i8h_gather_kernel<NMOD><<<dim3((unsigned)nmc, (unsigned)((nit * ntile_n + 3) / 4)), 128, 0, st>>>(rc, rc_ld, rc_plane, o, sp, kboff, cols, cols_off, m0,
+                                                                                                    nit, ntile_n, cg, cg_plane, rD, rd_plane, dcol);
 }
 
 // ---- GEMM ------------------------------------------------------------------------------------------------------------------
@@ -758,15 +702,13 @@ inline void i8h_tiling(int o, int cluster, int* nit, int* ntile_n) {
     *ntile_n = ((opw0 + *nit - 1) / *nit + ngran - 1) / ngran * ngran;
 }
 
-// The first J sweep can ride on the GEMM when the tiling has a free column behind the nocc orbitals and the 16-byte gather
-// (which knows about the density column) can run
+// The first J sweep can ride on the GEMM when the tiling has a free column behind the nocc orbitals
 inline bool i8h_can_fuse_col(const I8HalfPlan& pl, int o, int cluster) {
+    (void)pl;
     if (cluster != 2 && cluster != 4) cluster = 1;
     int nit, ntile_n;
     i8h_tiling(o, cluster, &nit, &ntile_n);
-    const char* e = getenv("B200JK_I8_GATHER");
-    const size_t rc_ld = (pl.kboff.size() - 1 + 127) / 128 * 128;
-    return o > 0 && o < nit * ntile_n && !(e && !strcmp(e, "word")) && i8g_smem_bytes(pl.max_nkb_row, rc_ld) <= I8G_SMEM_MAX;
+    return o > 0 && o < nit * ntile_n;
 }
 
 // bytes of arena one row-block with nkb k-blocks needs
@@ -973,26 +915,8 @@ inline int i8_half_run(I8HalfPlan& pl, cudaStream_t st, int nsm, const double* t
         }
         if (prof) cudaEventRecord(pl.prof[1], st);
         if (pl.mark) pl.mark(pl.mark_ctx, 11);
-        static int gather_word = -1;
-        if (gather_word < 0) {
-            const char* e = getenv("B200JK_I8_GATHER");
-            gather_word = (e && !strcmp(e, "word")) ? 1 : 0;
-        }
-        if (!fuse_col && (gather_word || i8g_smem_bytes(pl.max_nkb_row, rc_ld) > I8G_SMEM_MAX))
-            i8h_gather_kernel<<<dim3((unsigned)nmc, (unsigned)((opw + 3) / 4)), 128, 0, st>>>(pl.rc, rc_ld, rc_plane, o, nmod, d_sp, pl.d_kboff,
-                                                                                            d_cols, d_cols_off, c.m0, nit, ntile_n, cg, cg_plane);
-        else {
-            static bool gattr[64] = {false};  // per device
-            int dev = 0;
-            cudaGetDevice(&dev);
-            if (!gattr[dev & 63]) {
-                I8CK(cudaFuncSetAttribute(i8h_gather16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8G_SMEM_MAX));
-                gattr[dev & 63] = true;
-            }
-            i8h_gather16_kernel<<<dim3((unsigned)nmc, (unsigned)((opw + I8G_ROWS - 1) / I8G_ROWS)), 256, i8g_smem_bytes(pl.max_nkb_row, rc_ld),
-                                  st>>>(pl.rc, rc_ld, rc_plane, o, nmod, d_sp, pl.d_kboff, d_cols, d_cols_off, c.m0, nit, ntile_n, cg, cg_plane,
-                                        fuse_col ? pl.rD : nullptr, rd_plane, fuse_col ? o : -1, pl.max_nkb_row);
-        }
+        I8H_DISPATCH(nmod, i8h_launch_gather, pl.rc, rc_ld, rc_plane, o, d_sp, pl.d_kboff, d_cols, d_cols_off, c.m0, nmc, nit, ntile_n, cg, cg_plane,
+                     fuse_col ? pl.rD : nullptr, rd_plane, fuse_col ? o : -1, st);
         if (prof) cudaEventRecord(pl.prof[2], st);
         if (pl.mark) pl.mark(pl.mark_ctx, 12);
         I8HalfParams gp;

@@ -163,12 +163,12 @@ assert err < 1e-10
                                  {"B200JK_KGEMM": "i8", "B200JK_HALF": "i8", "B200JK_I8_CLUSTER": "4"},
                                  {"B200JK_HALF": "i8", "B200JK_I8_CLUSTER": "1", "B200JK_NO_JFUSE": "1",
                                   "B200JK_I8_HALF_MODULI": "13", "B200JK_I8_MODULI": "12"},
-                                 {"B200JK_HALF": "i8", "B200JK_I8_GATHER": "word"}, {"B200JK_HALF": "i8", "B200JK_I8_JCOL": "0"}])
+                                 {"B200JK_HALF": "i8", "B200JK_I8_JCOL": "0"}])
 def test_ab_switches_still_correct(tmp_path, env):
     """The A/B switches documented in DESIGN.md (first-generation kernels, unfused J, pre-gathered C^T forced on for a
     small screened system, with and without the density row riding in it, the INT8-tensor-core arms of the two GEMMs forced
-    from the environment with 1 / 2 / 4 CTAs per cluster, the word-wise C^T gather, the first J sweep as its own kernel
-    instead of a column of the residue GEMM) stay parity-green."""
+    from the environment with 1 / 2 / 4 CTAs per cluster, the first J sweep as its own kernel instead of a column of the
+    residue GEMM) stay parity-green."""
     script = tmp_path / "ab.py"
     script.write_text(LEGACY_SCRIPT)
     r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, B2_ROOT=ROOT, **env), capture_output=True,
