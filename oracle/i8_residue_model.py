@@ -173,3 +173,34 @@ def build_K(B_dense: np.ndarray, keep: np.ndarray, Cl: np.ndarray, Cr: np.ndarra
     if Cl.shape[1] == 0:
         return np.zeros((nbf, nbf))
     return matmul_nt(T1.reshape(nbf, -1), T2.reshape(nbf, -1), nmod_k)
+
+
+def build_J(B_dense: np.ndarray, keep: np.ndarray, D: np.ndarray, symmetric: bool, nmod: int = 12) -> np.ndarray:
+    """J of DFHelper::compute_J_symm / compute_J (lib3index/dfhelper.cc:3162-3283) with the FIRST sweep taken through the
+    residue arm, as the engine does when the sweep rides on the K3 GEMM (I8HalfFuseJ::gemm_col): per row-block m
+        d_part[m][q] = sum_{n kept} B[q, m, n] D'[m, n],   D' = the density row as j_prep_dm_kernel prepares it
+    (symmetric: 2 D above the diagonal, D on it, 0 below; general: D), d_Q = sum_m d_part[m][q] in row-block order, and the
+    second sweep J[m, n] = sum_Q B[Q, m, n] d_Q in double (j_mn_kernel), mirrored when symmetric."""
+    naux, nbf, _ = B_dense.shape
+    Dp = np.array(D, dtype=np.float64)
+    if symmetric:
+        Dp = np.triu(2.0 * Dp, 1) + np.diag(np.diag(D))
+    Rb = row_bound(nmod, nbf)
+    eD = row_exponents(Dp, Rb)  # full row norm, as the engine takes it
+    d = np.zeros(naux)
+    for m in range(nbf):
+        cols = np.flatnonzero(keep[m])
+        A = np.ascontiguousarray(B_dense[:, m, cols])
+        ea = row_exponents(A, Rb)
+        drow = Dp[m:m + 1, cols]
+        res = modular_products(residues(quantize(A, ea), nmod), residues(quantize(drow, eD[m:m + 1]), nmod))
+        d += np.ldexp(crt_fast(res)[:, 0], -(ea + eD[m]).astype(np.int64))
+    J = np.zeros((nbf, nbf))
+    for m in range(nbf):
+        for n in np.flatnonzero(keep[m]):
+            if symmetric and n < m:
+                continue
+            J[m, n] = float(np.dot(B_dense[:, m, n], d))
+            if symmetric:
+                J[n, m] = J[m, n]
+    return J

@@ -88,3 +88,22 @@ def test_residue_arms_reproduce_the_reference_golden_vectors():
         K = model.build_K(B, keep, Cl, Cr)
         worst = max(worst, float(np.abs(K - g[f"K_gen{i}"]).max()))
     assert worst < 1e-10, worst
+
+
+def test_first_j_sweep_through_the_residue_arm_reproduces_the_golden_j():
+    """The first J sweep as a column of the K3 residue GEMM (12 moduli, floating-point CRT, the density row scaled by its
+    full norm) followed by the FP64 second sweep: J of the reference's object code to 1e-10, symmetric and general."""
+    from psi4_b200 import DFHelper
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_jk_vectors.npz"))
+    keep = g["keep"].astype(bool)
+    n, a = keep.shape[0], int(g["naux"])
+    d = DFHelper(n, a)
+    d.prepare_sparsity(keep=keep)
+    B = d.unpack(g["Ppq"])
+    worst = 0.0
+    for i in range(len(g["noccs"])):
+        Cl, Cr = g[f"Cl{i}"], g[f"Cr{i}"]
+        worst = max(worst, float(np.abs(model.build_J(B, keep, Cl @ Cl.T, True) - g[f"J_sym{i}"]).max()))
+        worst = max(worst, float(np.abs(model.build_J(B, keep, Cl @ Cr.T, False) - g[f"J_gen{i}"]).max()))
+    assert worst < 1e-10, worst
