@@ -11,9 +11,14 @@ partial J/K are summed over NVLink inside the engine ("strong" scaling: total wo
                from CUDA events on the engine's stream, max over ranks
   e2e          ms per build through the host-pointer C ABI call b200jk_compute (what psi4's
                MemDFJK::compute_JK would call): pinned staging + H2D of C and D + D2H of J and K inside
-  roofline     dominant kernel = K3 half-transform (DMMA); denominators: FP64 DMMA ceiling measured
-               live by a register-resident m8n8k4 loop (MEASURED_PEAKS.json has no FP64 figure), with a
-               cuBLAS DGEMM of the K-GEMM's shape timed beside it as the library comparator
+  roofline     the dominant kernel of the timed builds with the roof that binds it.  On the default arms of this
+               workload (both GEMMs on the INT8 tensor cores by residues) that is the K3 residue GEMM, a stream of
+               the residue planes: algorithmic bytes / CUDA-event time against hbm_gbs of MEASURED_PEAKS.json, the
+               int8 tensor view (2 x the measured bf16 figure) beside it; kernels.*.int8_arm lists every sub-phase
+  roofline_fp64  K3 on the FP64 tensor pipe (what the north_star names), measured in the same run on the FP64
+               arms (`fp64_arms`): FP64 DMMA ceiling measured live by a register-resident m8n8k4 loop
+               (MEASURED_PEAKS.json has no FP64 figure), with a cuBLAS DGEMM of the K GEMM's shape timed beside
+               it as the library comparator
   parity_spot  outside the timed region, at every N: rows of J and a sample of K elements of rank 0's
                summed result recomputed on the host from the counter hash that defines the synthetic
                tensor (the oracle as CHECKER); the run exits non-zero above 1e-10
