@@ -173,8 +173,8 @@ def test_i8_golden_vectors():
 @pytest.mark.parametrize("kgemm", ["dmma", "i8"])
 def test_i8_half_transform_matches_oracle(oracle, lr, density, kgemm):
     """DFHelper::first_transform_pQq (lib3index/dfhelper.cc:2162-2186) by residues: screened and dense masks, ragged nocc
-    incl. 0 / 1 / odd, two different C matrices, with either arm of the K GEMM behind it.  The first J sweep rides on the
-    conversion of the tensor rows (I8HalfFuseJ)."""
+    incl. 0 / 1 / odd, two different C matrices, with either arm of the K GEMM behind it.  The first J sweep is a column of
+    the residue GEMM where the tiling has a free one (nocc 23, 1), its own kernel otherwise (nocc 64)."""
     rng = np.random.default_rng(21 + lr + int(10 * density))
     n, a = 300, 150
     keep = random_mask(rng, n, density)
